@@ -1,0 +1,258 @@
+/*
+ * pdegpu.h -- C ABI of libpdegpu, the B200-native (sm_100a) replacement for the iterative
+ * variational solver core of JediZ/PDE-based-image-processing (reference: mex/source/library/).
+ *
+ * Scope = SURVEY.md section 8: relaxation sweeps (point red-black SOR / zebra line SOR),
+ * residual / LHS operators, bilinear warp, Simoncelli derivatives, diffusion weights.
+ * Every entry point names the reference interface it replaces (file:line under /root/reference).
+ *
+ * Conventions (identical to the reference's MEX gateways):
+ *   - all arrays are fp32, dense, COLUMN-MAJOR (Matlab): element (i,j,k) of an
+ *     nrows x ncols x nframes array lives at  k*nrows*ncols + j*nrows + i
+ *     (reference opticalflowSolvers.c:81).
+ *   - `iter`, `omega` are passed as floats exactly as the gateways receive them; `iter`
+ *     is truncated to int like the reference does ((int)Mparam.iter, opticalflowSolvers.c:74).
+ *   - `solver`: 1 = point-wise Gauss-Seidel SOR, 2 = alternating line relaxation (ALR).
+ *     The reference runs both in lexicographic order, which is inherently serial; libpdegpu
+ *     runs the SAME fixed-point iteration in parallel orderings: solver 1 -> red-black
+ *     (4-colour for 8-neighbour stencils), solver 2 -> zebra (even lines, then odd lines).
+ *     Same linear system, same boundary model, same relaxation => same converged solution;
+ *     iterates differ at finite `iter` (BASELINE.json north_star: "agree at convergence").
+ *   - NaN in a data term (Cu/Du/TRACE) means "no data term at this pixel" exactly as in the
+ *     reference (opticalflowSolvers.c:118-149, disparitySolvers.c:96-112, pdeSolvers.c:101-114).
+ *   - No CPU fallback exists. Every function returns PDEGPU_OK (0) or a negative pdegpu_status;
+ *     pdegpu_last_error() gives the message. Nothing throws, nothing prints.
+ *
+ * Two families of entry points:
+ *   pdegpu_<name>(ctx, host pointers...)      drop-in for one MEX call: H2D, kernels, D2H.
+ *   pdegpu_dev_<name>(ctx, device pointers..) device-resident, asynchronous on the context's
+ *                                             stream, with a `batch` of independent problems;
+ *                                             used by fused pipelines, benchmarks, multi-GPU.
+ *
+ * Threading: one context per (host thread, GPU); a context must not be shared between threads.
+ */
+#ifndef PDEGPU_H
+#define PDEGPU_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEGPU_VERSION_MAJOR 0
+#define PDEGPU_VERSION_MINOR 1
+
+typedef enum pdegpu_status {
+    PDEGPU_OK              =  0,
+    PDEGPU_ERR_ARG         = -1,   /* null pointer, bad solver id, ...                       */
+    PDEGPU_ERR_SHAPE       = -2,   /* unsupported shape (e.g. nrows < 3 for a solver)         */
+    PDEGPU_ERR_CUDA        = -3,   /* CUDA runtime error, see pdegpu_last_error()             */
+    PDEGPU_ERR_NOMEM       = -4,   /* device or pinned-host allocation failed                 */
+    PDEGPU_ERR_NODEVICE    = -5,   /* no usable sm_100 GPU                                    */
+    PDEGPU_ERR_UNSUPPORTED = -6
+} pdegpu_status;
+
+typedef struct pdegpu_ctx pdegpu_ctx;
+
+/* ------------------------------------------------------------------------------------------
+ * Context
+ * ------------------------------------------------------------------------------------------ */
+int         pdegpu_device_count(void);                       /* number of visible CUDA devices (0 if none) */
+int         pdegpu_init(int device, pdegpu_ctx **ctx);       /* create a context + stream on `device`    */
+void        pdegpu_free(pdegpu_ctx *ctx);
+const char *pdegpu_last_error(const pdegpu_ctx *ctx);        /* ctx may be NULL: last error of pdegpu_init */
+const char *pdegpu_version(void);
+int         pdegpu_sync(pdegpu_ctx *ctx);                    /* wait for the context's stream           */
+void       *pdegpu_stream(pdegpu_ctx *ctx);                  /* the cudaStream_t, as void*              */
+/* Number of libpdegpu kernels launched through this context since creation (bench evidence). */
+unsigned long long pdegpu_launch_count(const pdegpu_ctx *ctx);
+/* Kernel generation: 0 = "simple" global-memory kernels (kept as an in-library cross-check),
+ * 1 = streaming register/shared-memory kernels (default). */
+int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);
+
+/* Device / pinned memory owned by the library (for the pdegpu_dev_* entry points). */
+int         pdegpu_malloc(pdegpu_ctx *ctx, void **dptr, size_t bytes);
+int         pdegpu_free_mem(pdegpu_ctx *ctx, void *dptr);
+int         pdegpu_host_alloc(pdegpu_ctx *ctx, void **hptr, size_t bytes);   /* pinned */
+int         pdegpu_host_free(pdegpu_ctx *ctx, void *hptr);
+int         pdegpu_upload(pdegpu_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* async */
+int         pdegpu_download(pdegpu_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async */
+
+/* ------------------------------------------------------------------------------------------
+ * Host-pointer, drop-in entry points: one per hot-path MEX gateway.
+ * Outputs are written completely (same contents the gateway's plhs[] would hold).
+ * ------------------------------------------------------------------------------------------ */
+
+/* [U V (RU RV)] = Oflow_sor_elin4_2d(U,V,M,Cu,Cv,Du,Dv,wW,wN,wE,wS,iter,omega,solver)
+ * replaces mexFunction in mex/source/Oflow_sor_elin4_2d.c:64-352, i.e.
+ * GS_SOR_elin4_2d (opticalflowSolvers.c:41) / GS_ALR_SOR_elin4_2d (:196) and
+ * Residuals_elin4_2d (:269).
+ * U_out,V_out: nrows x ncols. iter<=0 -> U_out,V_out are ZERO (gateway never copies, :341-346).
+ * RU,RV (may be NULL): nrows x ncols x nframes residuals of the INPUT U,V (:350), where
+ * M,Cu,Cv,Du,Dv may carry nframes>1 channels; the sweep itself uses channel 0 only. */
+int pdegpu_oflow_sor_elin4_2d(pdegpu_ctx *ctx,
+        float *U_out, float *V_out, float *RU, float *RV,
+        const float *U, const float *V, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver);
+
+/* [dU dV (RU RV)] = Oflow_sor_llin4_2d(U,V,dU,dV,M,Cu,Cv,Du,Dv,wW,wN,wE,wS,iter,omega,solver)
+ * replaces mex/source/Oflow_sor_llin4_2d.c (GS_SOR_llin4_2d opticalflowSolvers.c:504,
+ * GS_ALR_SOR_llin4_2d :690, Residuals_llin4_2d :766). Residuals are of the INPUT dU,dV. */
+int pdegpu_oflow_sor_llin4_2d(pdegpu_ctx *ctx,
+        float *dU_out, float *dV_out, float *RU, float *RV,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver);
+
+/* [dU dV] = Oflow_sor_llin8_2d(U,V,dU,dV,M,Cu,Cv,Du,Dv,wW,wNW,wN,wNE,wE,wSE,wS,wSW,iter,omega,solver)
+ * replaces mex/source/Oflow_sor_llin8_2d.c (GS_SOR_llin8_2d opticalflowSolvers.c:1487 -- which
+ * ignores the diagonal weights, SURVEY Q6 -- and GS_ALR_SOR_llin8_2d :1677). */
+int pdegpu_oflow_sor_llin8_2d(pdegpu_ctx *ctx,
+        float *dU_out, float *dV_out,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wNW, const float *wN, const float *wNE,
+        const float *wE, const float *wSE, const float *wS, const float *wSW,
+        int nrows, int ncols, float iter, float omega, int solver);
+
+/* [AU AV] = Oflow_lhs_elin4_2d(U,V,M,Du,Dv,wW,wN,wE,wS)
+ * replaces mex/source/Oflow_lhs_elin4_2d.c (LHS_elin4_2d opticalflowSolvers.c:387).
+ * M,Du,Dv: nrows x ncols x nframes; AU,AV the same. */
+int pdegpu_oflow_lhs_elin4_2d(pdegpu_ctx *ctx, float *AU, float *AV,
+        const float *U, const float *V, const float *M, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes);
+
+/* [AU AV] = Oflow_lhs_llin4_2d(U,V,dU,dV,M,Du,Dv,wW,wN,wE,wS)
+ * replaces mex/source/Oflow_lhs_llin4_2d.c (LHS_llin4_2d opticalflowSolvers.c:923), including its
+ * border-fill defect (north border row of AV is left 0 for columns 1..ncols-2). */
+int pdegpu_oflow_lhs_llin4_2d(pdegpu_ctx *ctx, float *AU, float *AV,
+        const float *U, const float *V, const float *dU, const float *dV,
+        const float *M, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes);
+
+/* [dU (RU)] = Disp_sor_llin4_2d(U,dU,Cu,Du,wW,wN,wE,wS,iter,omega,solver)
+ * replaces mex/source/Disp_sor_llin4_2d.c (GS_SOR_llin4_2d disparitySolvers.c:41,
+ * GS_ALR_SOR_llin4_2d :154). The reference allocates RU but never fills it
+ * (Disp_sor_llin4_2d.c:251-269): RU, when requested, is all zeros. */
+int pdegpu_disp_sor_llin4_2d(pdegpu_ctx *ctx, float *dU_out, float *RU,
+        const float *U, const float *dU, const float *Cu, const float *Du,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, float iter, float omega, int solver);
+
+/* [dU0 dU1] = Disp_sor_llin_sym4_2d(U0,dU0,Cu0,Du0,wW0,wN0,wE0,wS0,U1,dU1,...,iter,omega,solver)
+ * replaces mex/source/Disp_sor_llin_sym4_2d.c (GS_SOR_llinsym4_2d disparitySolvers.c:301,
+ * GS_ALR_SOR_llinsym4_2d :462): two independent scalar systems relaxed side by side. */
+int pdegpu_disp_sor_llin_sym4_2d(pdegpu_ctx *ctx, float *dU0_out, float *dU1_out,
+        const float *U0, const float *dU0, const float *Cu0, const float *Du0,
+        const float *wW0, const float *wN0, const float *wE0, const float *wS0,
+        const float *U1, const float *dU1, const float *Cu1, const float *Du1,
+        const float *wW1, const float *wN1, const float *wE1, const float *wS1,
+        int nrows, int ncols, float iter, float omega, int solver);
+
+/* X = PDEsolver4(X,TRACE,B,wW,wN,wE,wS,iter,omega,solver)
+ * replaces mex/source/PDEsolver4.c (GS_SOR_4_2d pdeSolvers.c:44, GS_ALR_SOR_4_2d :277).
+ * All arrays nrows x ncols x nframes; frames are independent systems. */
+int pdegpu_pdesolver4(pdegpu_ctx *ctx, float *X_out,
+        const float *X, const float *TRACE, const float *B,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver);
+
+/* X = PDEsolver8(X,TRACE,B,wW,wNW,wN,wNE,wE,wSE,wS,wSW,iter,omega,solver)
+ * replaces mex/source/PDEsolver8.c (GS_SOR_8_2d pdeSolvers.c:153, GS_ALR_SOR_8_2d :344).
+ * Reference quirks kept: solver 2 performs ONE iteration whatever `iter` is (pdeSolvers.c:362,
+ * SURVEY Q4), relaxes interior lines only (:1155,:1290) and its NaN-TRACE diagonal counts wNW
+ * twice and wNE never (:1179). */
+int pdegpu_pdesolver8(pdegpu_ctx *ctx, float *X_out,
+        const float *X, const float *TRACE, const float *B,
+        const float *wW, const float *wNW, const float *wN, const float *wNE,
+        const float *wE, const float *wSE, const float *wS, const float *wSW,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver);
+
+/* Iout = BilinInterp_2d(Iin,X,Y)
+ * replaces mex/source/BilinInterp_2d.c (bilinInterp2 imageInterpolation.c:44).
+ * (X,Y) are 1-based Matlab coordinates, X along columns, Y along rows. `oob_value` is written
+ * where the look-up falls outside the image: the reference's 5th parameter, which its own
+ * gateway forgets to pass -- the libpdegpu gateway passes NaN, the author's intent. */
+int pdegpu_bilin_interp_2d(pdegpu_ctx *ctx, float *Iout,
+        const float *Iin, const float *X, const float *Y,
+        int nrows, int ncols, int nframes, float oob_value);
+
+/* [Idt Idx Idy] = FstDerivatives5(It0,It1)
+ * replaces mex/source/FstDerivatives5.c (fstSimoncelli_c imageDerivatives.c:309, 5-tap path). */
+int pdegpu_fst_derivatives5(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes);
+
+/* [Idxt Idyt Idxx Idyy Idxy] = SndDerivatives5(It0,It1)
+ * replaces mex/source/SndDerivatives5.c (sndSimoncelli_c imageDerivatives.c:391). */
+int pdegpu_snd_derivatives5(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes);
+
+/* [wW wN wE wS] = DdiffWeights(D,eps)
+ * replaces mex/source/DdiffWeights.c (diffWeights6_2D_c imageDiffusionWeights.c:341).
+ * D: nrows x ncols x nframes; outputs: nrows x ncols (max over frames), outward edges 0. */
+int pdegpu_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS,
+        const float *D, int nrows, int ncols, int nframes, float eps);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-pointer entry points (asynchronous on pdegpu_stream(ctx)).
+ * `batch` independent problems of identical shape; problem b of every array starts at
+ * ptr + b*batch_stride (elements). For multi-frame arrays of ONE problem use the host API or
+ * set batch = nframes where frames are independent (PDE solvers).
+ * ------------------------------------------------------------------------------------------ */
+
+typedef enum pdegpu_family {
+    PDEGPU_FLOW_ELIN4 = 0,   /* unknowns U,V                       (opticalflowSolvers.c:41,196)   */
+    PDEGPU_FLOW_LLIN4 = 1,   /* unknowns dU,dV; fixed U,V          (:504,:690)                      */
+    PDEGPU_FLOW_LLIN8 = 2,   /* 8-neighbour late-lin               (:1487,:1677)                    */
+    PDEGPU_DISP_LLIN4 = 3,   /* unknown dU; fixed U                (disparitySolvers.c:41,154)      */
+    PDEGPU_PDE4       = 4,   /* unknown X; TRACE,B                 (pdeSolvers.c:44,277)            */
+    PDEGPU_PDE8       = 5    /* 8-neighbour                        (pdeSolvers.c:153,344)           */
+} pdegpu_family;
+
+/* One linear system family instance in device memory. Unused pointers are NULL.
+ *   x[0],x[1] : unknowns, relaxed IN PLACE (U,V | dU,dV | dU | X)
+ *   x0[0],x0[1]: fixed fields of the late-linearisation families (U,V | U)
+ *   m          : coupling term M (flow families)
+ *   c[0],c[1]  : Cu,Cv | Cu | B
+ *   d[0],d[1]  : Du,Dv | Du | TRACE
+ *   w[8]       : wW,wN,wE,wS,wNW,wNE,wSE,wSW  */
+typedef struct pdegpu_system {
+    int family;
+    int nrows, ncols, batch;
+    long long batch_stride;
+    float *x[2];
+    const float *x0[2];
+    const float *m;
+    const float *c[2];
+    const float *d[2];
+    const float *w[8];
+} pdegpu_system;
+
+/* Run `iter` relaxation iterations of `solver` (1 point red-black, 2 zebra line) in place. */
+int pdegpu_dev_relax(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);
+
+/* r = b - A x (elin4 / llin4 flow families), Residuals_* semantics incl. border replication.
+ * c,d,m may have `nframes` channels per problem (channel stride nrows*ncols); x,x0,w have one. */
+int pdegpu_dev_residual(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV);
+/* A x (LHS_* semantics). */
+int pdegpu_dev_lhs(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *AU, float *AV);
+
+int pdegpu_dev_bilin_interp_2d(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y,
+        int nrows, int ncols, int nframes, float oob_value);
+int pdegpu_dev_fst_derivatives5(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes);
+int pdegpu_dev_snd_derivatives5(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes);
+int pdegpu_dev_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS,
+        const float *D, int nrows, int ncols, int nframes, float eps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEGPU_H */

@@ -1,0 +1,507 @@
+// api.cu -- the extern "C" surface of libpdegpu (see include/pdegpu.h).
+//   pdegpu_dev_*  : validation + dispatch to the kernel launchers (asynchronous).
+//   pdegpu_<name> : one MEX gateway call: stage host arrays into the context's device arena,
+//                   run the device path, copy the outputs back, synchronise.
+#include "pdegpu_internal.cuh"
+#include <initializer_list>
+
+// ---------------------------------------------------------------------------------------------
+// device-pointer API
+// ---------------------------------------------------------------------------------------------
+static int check_system(pdegpu_ctx *ctx, const pdegpu_system *s, const char *who)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!s) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: system is NULL", who);
+    if (s->family < PDEGPU_FLOW_ELIN4 || s->family > PDEGPU_PDE8) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: unknown family %d", who, s->family);
+    if (s->nrows < 3 || s->ncols < 3) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: need nrows,ncols >= 3 (got %d x %d)", who, s->nrows, s->ncols);
+    if (s->batch < 1 || s->batch > 65535) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: batch must be in [1,65535]", who);
+    if (s->batch > 1 && s->batch_stride < (long long)s->nrows * s->ncols) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: batch_stride smaller than one field", who);
+    const bool two = s->family <= PDEGPU_FLOW_LLIN8;
+    const bool late = s->family >= PDEGPU_FLOW_LLIN4 && s->family <= PDEGPU_DISP_LLIN4;
+    const bool eight = s->family == PDEGPU_FLOW_LLIN8 || s->family == PDEGPU_PDE8;
+    const int nunk = two ? 2 : 1;
+    for (int q = 0; q < nunk; q++) {
+        if (!s->x[q] || !s->c[q] || !s->d[q]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: x/c/d[%d] is NULL", who, q);
+        if (late && !s->x0[q]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: x0[%d] is NULL", who, q);
+    }
+    if (two && !s->m) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: m is NULL", who);
+    for (int n = 0; n < (eight ? 8 : 4); n++)
+        if (!s->w[n]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: w[%d] is NULL", who, n);
+    return PDEGPU_OK;
+}
+
+extern "C" int pdegpu_dev_relax(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver)
+{
+    int rc = check_system(ctx, sys, "pdegpu_dev_relax");
+    if (rc) return rc;
+    if (solver != 1 && solver != 2) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_relax: no such solver %d", solver);
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (iter <= 0 && !(sys->family == PDEGPU_PDE8 && solver == 2)) return PDEGPU_OK;
+    if (ctx->kernel_path == 1) {
+        rc = relax_stream(ctx, sys, iter, omega, solver);
+        if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
+    }
+    return relax_simple(ctx, sys, iter, omega, solver);
+}
+
+extern "C" int pdegpu_dev_residual(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV)
+{
+    int rc = check_system(ctx, sys, "pdegpu_dev_residual");
+    if (rc) return rc;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_residual(ctx, sys, nframes, RU, RV, false);
+}
+
+extern "C" int pdegpu_dev_lhs(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *AU, float *AV)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!sys) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_lhs: system is NULL");
+    // LHS needs no c[] terms
+    pdegpu_system tmp = *sys;
+    if (!tmp.c[0]) tmp.c[0] = tmp.d[0];
+    if (!tmp.c[1]) tmp.c[1] = tmp.d[1];
+    int rc = check_system(ctx, &tmp, "pdegpu_dev_lhs");
+    if (rc) return rc;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_residual(ctx, &tmp, nframes, AU, AV, true);
+}
+
+extern "C" int pdegpu_dev_bilin_interp_2d(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y,
+                                          int nrows, int ncols, int nframes, float oob_value)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_bilin(ctx, Iout, Iin, X, Y, nrows, ncols, nframes, oob_value);
+}
+
+extern "C" int pdegpu_dev_fst_derivatives5(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy,
+                                           const float *It0, const float *It1, int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_fst(ctx, Idt, Idx, Idy, It0, It1, nrows, ncols, nframes);
+}
+
+extern "C" int pdegpu_dev_snd_derivatives5(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy,
+                                           const float *It0, const float *It1, int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_snd(ctx, Idxt, Idyt, Idxx, Idyy, Idxy, It0, It1, nrows, ncols, nframes);
+}
+
+extern "C" int pdegpu_dev_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS,
+                                        const float *D, int nrows, int ncols, int nframes, float eps)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return op_ddiff(ctx, wW, wN, wE, wS, D, nrows, ncols, nframes, eps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer API
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// Stages one MEX call's arrays through the context's arena.
+struct HostCall {
+    pdegpu_ctx *ctx;
+    int rc;
+    HostCall(pdegpu_ctx *c, size_t total_floats, int narrays) : ctx(c), rc(PDEGPU_OK)
+    {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) { rc = pdegpu_check_cuda(ctx, e, "cudaSetDevice"); return; }
+        pdegpu_arena_reset(ctx);
+        rc = pdegpu_arena_reserve(ctx, total_floats * sizeof(float) + 256 * (size_t)(narrays + 1));
+    }
+    float *in(const float *h, size_t n)
+    {
+        if (rc) return nullptr;
+        float *d = (float *)pdegpu_arena_alloc(ctx, n * sizeof(float));
+        if (!d) { rc = pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "device arena exhausted"); return nullptr; }
+        cudaError_t e = cudaMemcpyAsync(d, h, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { rc = pdegpu_check_cuda(ctx, e, "cudaMemcpyAsync(H2D)"); return nullptr; }
+        return d;
+    }
+    float *out(size_t n, bool zero)
+    {
+        if (rc) return nullptr;
+        float *d = (float *)pdegpu_arena_alloc(ctx, n * sizeof(float));
+        if (!d) { rc = pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "device arena exhausted"); return nullptr; }
+        if (zero) {
+            cudaError_t e = cudaMemsetAsync(d, 0, n * sizeof(float), ctx->stream);
+            if (e != cudaSuccess) { rc = pdegpu_check_cuda(ctx, e, "cudaMemsetAsync"); return nullptr; }
+        }
+        return d;
+    }
+    void fetch(float *h, const float *d, size_t n)
+    {
+        if (rc) return;
+        cudaError_t e = cudaMemcpyAsync(h, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) rc = pdegpu_check_cuda(ctx, e, "cudaMemcpyAsync(D2H)");
+    }
+    int finish()
+    {
+        if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaStreamSynchronize");
+        return PDEGPU_OK;
+    }
+};
+
+int check_host(pdegpu_ctx *ctx, const char *who, int nrows, int ncols, int nframes, int solver, bool has_solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (nrows < 3 || ncols < 3) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: need nrows,ncols >= 3 (got %d x %d)", who, nrows, ncols);
+    if (nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: nframes < 1", who);
+    if (has_solver && solver != 1 && solver != 2) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: no such solver", who);
+    return PDEGPU_OK;
+}
+
+bool any_null(std::initializer_list<const void *> ps)
+{
+    for (const void *p : ps) if (!p) return true;
+    return false;
+}
+
+}  // namespace
+
+#define NULLCHECK(who, ...) \
+    if (any_null({__VA_ARGS__})) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, who ": null pointer argument")
+
+// common body of the two 4-neighbour flow gateways
+static int flow_sor4(pdegpu_ctx *ctx, const char *who, int family,
+                     float *o0, float *o1, float *RU, float *RV,
+                     const float *U, const float *V, const float *dU, const float *dV, const float *M,
+                     const float *Cu, const float *Cv, const float *Du, const float *Dv,
+                     const float *wW, const float *wN, const float *wE, const float *wS,
+                     int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    int rc = check_host(ctx, who, nrows, ncols, nframes, solver, true);
+    if (rc) return rc;
+    const bool late = family == PDEGPU_FLOW_LLIN4;
+    const bool want_res = RU && RV;
+    const size_t n = (size_t)nrows * ncols, nf = want_res ? n * nframes : n;   // data terms: all frames only for residuals
+    const int it = (int)iter;
+    HostCall hc(ctx, (late ? 4 : 2) * n + 5 * nf + 4 * n + 2 * n + (want_res ? 2 * nf : 0), 20);
+    pdegpu_system s;
+    memset(&s, 0, sizeof(s));
+    s.family = family; s.nrows = nrows; s.ncols = ncols; s.batch = 1; s.batch_stride = (long long)n;
+    // the unknowns of the residual are the INPUTS (Oflow_sor_elin4_2d.c:350); the sweep works on a copy
+    float *xin0 = hc.in(late ? dU : U, n), *xin1 = hc.in(late ? dV : V, n);
+    if (late) { s.x0[0] = hc.in(U, n); s.x0[1] = hc.in(V, n); }
+    s.m = hc.in(M, nf);
+    s.c[0] = hc.in(Cu, nf); s.c[1] = hc.in(Cv, nf);
+    s.d[0] = hc.in(Du, nf); s.d[1] = hc.in(Dv, nf);
+    s.w[W_W] = hc.in(wW, n); s.w[W_N] = hc.in(wN, n); s.w[W_E] = hc.in(wE, n); s.w[W_S] = hc.in(wS, n);
+    float *x0 = hc.out(n, it <= 0), *x1 = hc.out(n, it <= 0);
+    float *dRU = nullptr, *dRV = nullptr;
+    if (want_res) { dRU = hc.out(nf, false); dRV = hc.out(nf, false); }
+    if (hc.rc) return hc.finish();
+    if (want_res) {
+        s.x[0] = xin0; s.x[1] = xin1;
+        if ((rc = op_residual(ctx, &s, nframes, dRU, dRV, false))) { hc.rc = rc; return hc.finish(); }
+        if (late && nframes > 1 && (rc = op_llin4_quirks(ctx, &s, nframes, dRU, dRV, false))) { hc.rc = rc; return hc.finish(); }
+    }
+    if (it > 0) {
+        // gateway: memcpy(U_out, U_in) then relax in place (Oflow_sor_elin4_2d.c:341-346)
+        cudaError_t e = cudaMemcpyAsync(x0, xin0, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(x1, xin1, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) { hc.rc = pdegpu_check_cuda(ctx, e, "cudaMemcpyAsync(D2D)"); return hc.finish(); }
+        s.x[0] = x0; s.x[1] = x1;
+        if ((rc = pdegpu_dev_relax(ctx, &s, it, omega, solver))) { hc.rc = rc; return hc.finish(); }
+    }
+    hc.fetch(o0, x0, n); hc.fetch(o1, x1, n);
+    if (want_res) { hc.fetch(RU, dRU, nf); hc.fetch(RV, dRV, nf); }
+    return hc.finish();
+}
+
+extern "C" int pdegpu_oflow_sor_elin4_2d(pdegpu_ctx *ctx,
+        float *U_out, float *V_out, float *RU, float *RV,
+        const float *U, const float *V, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_sor_elin4_2d", U_out, V_out, U, V, M, Cu, Cv, Du, Dv, wW, wN, wE, wS);
+    return flow_sor4(ctx, "pdegpu_oflow_sor_elin4_2d", PDEGPU_FLOW_ELIN4, U_out, V_out, RU, RV,
+                     U, V, nullptr, nullptr, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, nrows, ncols, nframes, iter, omega, solver);
+}
+
+extern "C" int pdegpu_oflow_sor_llin4_2d(pdegpu_ctx *ctx,
+        float *dU_out, float *dV_out, float *RU, float *RV,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_sor_llin4_2d", dU_out, dV_out, U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS);
+    return flow_sor4(ctx, "pdegpu_oflow_sor_llin4_2d", PDEGPU_FLOW_LLIN4, dU_out, dV_out, RU, RV,
+                     U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, nrows, ncols, nframes, iter, omega, solver);
+}
+
+extern "C" int pdegpu_oflow_sor_llin8_2d(pdegpu_ctx *ctx,
+        float *dU_out, float *dV_out,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wNW, const float *wN, const float *wNE,
+        const float *wE, const float *wSE, const float *wS, const float *wSW,
+        int nrows, int ncols, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_sor_llin8_2d", dU_out, dV_out, U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wNW, wN, wNE, wE, wSE, wS, wSW);
+    int rc = check_host(ctx, "pdegpu_oflow_sor_llin8_2d", nrows, ncols, 1, solver, true);
+    if (rc) return rc;
+    const size_t n = (size_t)nrows * ncols;
+    const int it = (int)iter;
+    HostCall hc(ctx, 19 * n, 20);
+    pdegpu_system s;
+    memset(&s, 0, sizeof(s));
+    s.family = PDEGPU_FLOW_LLIN8; s.nrows = nrows; s.ncols = ncols; s.batch = 1; s.batch_stride = (long long)n;
+    float *x0 = hc.out(n, it <= 0), *x1 = hc.out(n, it <= 0);
+    if (it > 0 && !hc.rc) {
+        cudaError_t e = cudaMemcpyAsync(x0, dU, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(x1, dV, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) hc.rc = pdegpu_check_cuda(ctx, e, "cudaMemcpyAsync(H2D)");
+        s.x[0] = x0; s.x[1] = x1;
+        s.x0[0] = hc.in(U, n); s.x0[1] = hc.in(V, n);
+        s.m = hc.in(M, n);
+        s.c[0] = hc.in(Cu, n); s.c[1] = hc.in(Cv, n); s.d[0] = hc.in(Du, n); s.d[1] = hc.in(Dv, n);
+        s.w[W_W] = hc.in(wW, n); s.w[W_N] = hc.in(wN, n); s.w[W_E] = hc.in(wE, n); s.w[W_S] = hc.in(wS, n);
+        s.w[W_NW] = hc.in(wNW, n); s.w[W_NE] = hc.in(wNE, n); s.w[W_SE] = hc.in(wSE, n); s.w[W_SW] = hc.in(wSW, n);
+        if (!hc.rc && (rc = pdegpu_dev_relax(ctx, &s, it, omega, solver))) hc.rc = rc;
+    }
+    hc.fetch(dU_out, x0, n); hc.fetch(dV_out, x1, n);
+    return hc.finish();
+}
+
+static int flow_lhs(pdegpu_ctx *ctx, const char *who, int family, float *AU, float *AV,
+                    const float *U, const float *V, const float *dU, const float *dV,
+                    const float *M, const float *Du, const float *Dv,
+                    const float *wW, const float *wN, const float *wE, const float *wS,
+                    int nrows, int ncols, int nframes)
+{
+    int rc = check_host(ctx, who, nrows, ncols, nframes, 0, false);
+    if (rc) return rc;
+    const bool late = family == PDEGPU_FLOW_LLIN4;
+    const size_t n = (size_t)nrows * ncols, nf = n * nframes;
+    HostCall hc(ctx, (late ? 4 : 2) * n + 3 * nf + 4 * n + 2 * nf, 16);
+    pdegpu_system s;
+    memset(&s, 0, sizeof(s));
+    s.family = family; s.nrows = nrows; s.ncols = ncols; s.batch = 1; s.batch_stride = (long long)n;
+    s.x[0] = hc.in(late ? dU : U, n); s.x[1] = hc.in(late ? dV : V, n);
+    if (late) { s.x0[0] = hc.in(U, n); s.x0[1] = hc.in(V, n); }
+    s.m = hc.in(M, nf);
+    s.d[0] = hc.in(Du, nf); s.d[1] = hc.in(Dv, nf);
+    s.c[0] = s.d[0]; s.c[1] = s.d[1];
+    s.w[W_W] = hc.in(wW, n); s.w[W_N] = hc.in(wN, n); s.w[W_E] = hc.in(wE, n); s.w[W_S] = hc.in(wS, n);
+    float *dAU = hc.out(nf, false), *dAV = hc.out(nf, false);
+    if (hc.rc) return hc.finish();
+    if ((rc = op_residual(ctx, &s, nframes, dAU, dAV, true))) { hc.rc = rc; return hc.finish(); }
+    if (late && (rc = op_llin4_quirks(ctx, &s, nframes, dAU, dAV, true))) { hc.rc = rc; return hc.finish(); }
+    hc.fetch(AU, dAU, nf); hc.fetch(AV, dAV, nf);
+    return hc.finish();
+}
+
+extern "C" int pdegpu_oflow_lhs_elin4_2d(pdegpu_ctx *ctx, float *AU, float *AV,
+        const float *U, const float *V, const float *M, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_lhs_elin4_2d", AU, AV, U, V, M, Du, Dv, wW, wN, wE, wS);
+    return flow_lhs(ctx, "pdegpu_oflow_lhs_elin4_2d", PDEGPU_FLOW_ELIN4, AU, AV, U, V, nullptr, nullptr, M, Du, Dv, wW, wN, wE, wS, nrows, ncols, nframes);
+}
+
+extern "C" int pdegpu_oflow_lhs_llin4_2d(pdegpu_ctx *ctx, float *AU, float *AV,
+        const float *U, const float *V, const float *dU, const float *dV,
+        const float *M, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_lhs_llin4_2d", AU, AV, U, V, dU, dV, M, Du, Dv, wW, wN, wE, wS);
+    return flow_lhs(ctx, "pdegpu_oflow_lhs_llin4_2d", PDEGPU_FLOW_LLIN4, AU, AV, U, V, dU, dV, M, Du, Dv, wW, wN, wE, wS, nrows, ncols, nframes);
+}
+
+// scalar late-linearisation system (disparity). `always_copy`: the symmetric gateway copies the
+// initial guess whatever `iter` is (Disp_sor_llin_sym4_2d.c:418-419), the plain one only for iter>0
+// (Disp_sor_llin4_2d.c:276-279).
+static int disp_stage(HostCall &hc, pdegpu_system &s, float *&xout,
+                      const float *U, const float *dU, const float *Cu, const float *Du,
+                      const float *wW, const float *wN, const float *wE, const float *wS,
+                      int nrows, int ncols, bool copy_guess)
+{
+    const size_t n = (size_t)nrows * ncols;
+    memset(&s, 0, sizeof(s));
+    s.family = PDEGPU_DISP_LLIN4; s.nrows = nrows; s.ncols = ncols; s.batch = 1; s.batch_stride = (long long)n;
+    xout = hc.out(n, !copy_guess);
+    if (copy_guess && !hc.rc) {
+        cudaError_t e = cudaMemcpyAsync(xout, dU, n * sizeof(float), cudaMemcpyHostToDevice, hc.ctx->stream);
+        if (e != cudaSuccess) hc.rc = pdegpu_check_cuda(hc.ctx, e, "cudaMemcpyAsync(H2D)");
+    }
+    s.x[0] = xout;
+    s.x0[0] = hc.in(U, n);
+    s.c[0] = hc.in(Cu, n); s.d[0] = hc.in(Du, n);
+    s.w[W_W] = hc.in(wW, n); s.w[W_N] = hc.in(wN, n); s.w[W_E] = hc.in(wE, n); s.w[W_S] = hc.in(wS, n);
+    return hc.rc;
+}
+
+extern "C" int pdegpu_disp_sor_llin4_2d(pdegpu_ctx *ctx, float *dU_out, float *RU,
+        const float *U, const float *dU, const float *Cu, const float *Du,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_disp_sor_llin4_2d", dU_out, U, dU, Cu, Du, wW, wN, wE, wS);
+    int rc = check_host(ctx, "pdegpu_disp_sor_llin4_2d", nrows, ncols, 1, solver, true);
+    if (rc) return rc;
+    const size_t n = (size_t)nrows * ncols;
+    const int it = (int)iter;
+    HostCall hc(ctx, 9 * n, 10);
+    pdegpu_system s;
+    float *xout = nullptr;
+    disp_stage(hc, s, xout, U, dU, Cu, Du, wW, wN, wE, wS, nrows, ncols, it > 0);
+    if (!hc.rc && it > 0 && (rc = pdegpu_dev_relax(ctx, &s, it, omega, solver))) hc.rc = rc;
+    hc.fetch(dU_out, xout, n);
+    rc = hc.finish();
+    // the reference allocates RU and never fills it (Disp_sor_llin4_2d.c:251-269)
+    if (!rc && RU) memset(RU, 0, n * sizeof(float));
+    return rc;
+}
+
+extern "C" int pdegpu_disp_sor_llin_sym4_2d(pdegpu_ctx *ctx, float *dU0_out, float *dU1_out,
+        const float *U0, const float *dU0, const float *Cu0, const float *Du0,
+        const float *wW0, const float *wN0, const float *wE0, const float *wS0,
+        const float *U1, const float *dU1, const float *Cu1, const float *Du1,
+        const float *wW1, const float *wN1, const float *wE1, const float *wS1,
+        int nrows, int ncols, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_disp_sor_llin_sym4_2d", dU0_out, dU1_out, U0, dU0, Cu0, Du0, wW0, wN0, wE0, wS0, U1, dU1, Cu1, Du1, wW1, wN1, wE1, wS1);
+    int rc = check_host(ctx, "pdegpu_disp_sor_llin_sym4_2d", nrows, ncols, 1, solver, true);
+    if (rc) return rc;
+    const size_t n = (size_t)nrows * ncols;
+    const int it = (int)iter;
+    HostCall hc(ctx, 18 * n, 20);
+    pdegpu_system s0, s1;
+    float *x0 = nullptr, *x1 = nullptr;
+    disp_stage(hc, s0, x0, U0, dU0, Cu0, Du0, wW0, wN0, wE0, wS0, nrows, ncols, true);
+    disp_stage(hc, s1, x1, U1, dU1, Cu1, Du1, wW1, wN1, wE1, wS1, nrows, ncols, true);
+    // the two systems are independent (disparitySolvers.c:373-422): relax one after the other
+    if (!hc.rc && it > 0 && (rc = pdegpu_dev_relax(ctx, &s0, it, omega, solver))) hc.rc = rc;
+    if (!hc.rc && it > 0 && (rc = pdegpu_dev_relax(ctx, &s1, it, omega, solver))) hc.rc = rc;
+    hc.fetch(dU0_out, x0, n); hc.fetch(dU1_out, x1, n);
+    return hc.finish();
+}
+
+static int pde_solve(pdegpu_ctx *ctx, const char *who, int family, float *X_out,
+                     const float *X, const float *TRACE, const float *B, const float *const w[8],
+                     int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    int rc = check_host(ctx, who, nrows, ncols, nframes, solver, true);
+    if (rc) return rc;
+    const int nw = family == PDEGPU_PDE8 ? 8 : 4;
+    const size_t n = (size_t)nrows * ncols * nframes;
+    HostCall hc(ctx, (3 + nw) * n, 12);
+    pdegpu_system s;
+    memset(&s, 0, sizeof(s));
+    s.family = family; s.nrows = nrows; s.ncols = ncols; s.batch = nframes; s.batch_stride = (long long)nrows * ncols;
+    float *x = hc.in(X, n);                                // memcpy(Xnew, Xold) then in place (PDEsolver4.c:239)
+    s.x[0] = x;
+    s.d[0] = hc.in(TRACE, n); s.c[0] = hc.in(B, n);
+    for (int k = 0; k < nw; k++) s.w[k] = hc.in(w[k], n);
+    if (!hc.rc && (rc = pdegpu_dev_relax(ctx, &s, (int)iter, omega, solver))) hc.rc = rc;
+    hc.fetch(X_out, x, n);
+    return hc.finish();
+}
+
+extern "C" int pdegpu_pdesolver4(pdegpu_ctx *ctx, float *X_out,
+        const float *X, const float *TRACE, const float *B,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_pdesolver4", X_out, X, TRACE, B, wW, wN, wE, wS);
+    const float *w[8] = {wW, wN, wE, wS, nullptr, nullptr, nullptr, nullptr};
+    return pde_solve(ctx, "pdegpu_pdesolver4", PDEGPU_PDE4, X_out, X, TRACE, B, w, nrows, ncols, nframes, iter, omega, solver);
+}
+
+extern "C" int pdegpu_pdesolver8(pdegpu_ctx *ctx, float *X_out,
+        const float *X, const float *TRACE, const float *B,
+        const float *wW, const float *wNW, const float *wN, const float *wNE,
+        const float *wE, const float *wSE, const float *wS, const float *wSW,
+        int nrows, int ncols, int nframes, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_pdesolver8", X_out, X, TRACE, B, wW, wNW, wN, wNE, wE, wSE, wS, wSW);
+    const float *w[8] = {wW, wN, wE, wS, wNW, wNE, wSE, wSW};
+    return pde_solve(ctx, "pdegpu_pdesolver8", PDEGPU_PDE8, X_out, X, TRACE, B, w, nrows, ncols, nframes, iter, omega, solver);
+}
+
+extern "C" int pdegpu_bilin_interp_2d(pdegpu_ctx *ctx, float *Iout,
+        const float *Iin, const float *X, const float *Y,
+        int nrows, int ncols, int nframes, float oob_value)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_bilin_interp_2d", Iout, Iin, X, Y);
+    if (nrows < 1 || ncols < 1 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_bilin_interp_2d: empty array");
+    const size_t n = (size_t)nrows * ncols;
+    HostCall hc(ctx, 2 * n * nframes + 2 * n, 5);
+    float *dI = hc.in(Iin, n * nframes), *dX = hc.in(X, n), *dY = hc.in(Y, n), *dO = hc.out(n * nframes, false);
+    int rc;
+    if (!hc.rc && (rc = op_bilin(ctx, dO, dI, dX, dY, nrows, ncols, nframes, oob_value))) hc.rc = rc;
+    hc.fetch(Iout, dO, n * nframes);
+    return hc.finish();
+}
+
+extern "C" int pdegpu_fst_derivatives5(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_fst_derivatives5", Idt, Idx, Idy, It0, It1);
+    if (nrows < 5 || ncols < 5 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_fst_derivatives5: need nrows,ncols >= 5");
+    const size_t n = (size_t)nrows * ncols * nframes;
+    HostCall hc(ctx, 5 * n, 6);
+    float *d0 = hc.in(It0, n), *d1 = hc.in(It1, n), *o0 = hc.out(n, false), *o1 = hc.out(n, false), *o2 = hc.out(n, false);
+    int rc;
+    if (!hc.rc && (rc = op_fst(ctx, o0, o1, o2, d0, d1, nrows, ncols, nframes))) hc.rc = rc;
+    hc.fetch(Idt, o0, n); hc.fetch(Idx, o1, n); hc.fetch(Idy, o2, n);
+    return hc.finish();
+}
+
+extern "C" int pdegpu_snd_derivatives5(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy,
+        const float *It0, const float *It1, int nrows, int ncols, int nframes)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_snd_derivatives5", Idxt, Idyt, Idxx, Idyy, Idxy, It0, It1);
+    if (nrows < 5 || ncols < 5 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_snd_derivatives5: need nrows,ncols >= 5");
+    const size_t n = (size_t)nrows * ncols * nframes;
+    HostCall hc(ctx, 7 * n, 8);
+    float *d0 = hc.in(It0, n), *d1 = hc.in(It1, n);
+    float *o[5];
+    for (int k = 0; k < 5; k++) o[k] = hc.out(n, false);
+    int rc;
+    if (!hc.rc && (rc = op_snd(ctx, o[0], o[1], o[2], o[3], o[4], d0, d1, nrows, ncols, nframes))) hc.rc = rc;
+    hc.fetch(Idxt, o[0], n); hc.fetch(Idyt, o[1], n); hc.fetch(Idxx, o[2], n); hc.fetch(Idyy, o[3], n); hc.fetch(Idxy, o[4], n);
+    return hc.finish();
+}
+
+extern "C" int pdegpu_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS,
+        const float *D, int nrows, int ncols, int nframes, float eps)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_ddiff_weights", wW, wN, wE, wS, D);
+    if (nrows < 2 || ncols < 2 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_ddiff_weights: need nrows,ncols >= 2");
+    const size_t n = (size_t)nrows * ncols;
+    HostCall hc(ctx, n * nframes + 4 * n, 6);
+    float *dD = hc.in(D, n * nframes);
+    float *o[4];
+    for (int k = 0; k < 4; k++) o[k] = hc.out(n, false);
+    int rc;
+    if (!hc.rc && (rc = op_ddiff(ctx, o[0], o[1], o[2], o[3], dD, nrows, ncols, nframes, eps))) hc.rc = rc;
+    hc.fetch(wW, o[0], n); hc.fetch(wN, o[1], n); hc.fetch(wE, o[2], n); hc.fetch(wS, o[3], n);
+    return hc.finish();
+}

@@ -1,0 +1,100 @@
+// pdegpu_internal.cuh -- shared declarations of libpdegpu's translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/pdegpu.h"
+
+// ------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------
+struct pdegpu_ctx {
+    int           device;
+    int           sm_count;
+    cudaStream_t  stream;
+    // growable device arena used by the host-pointer entry points (one bump allocation per call)
+    char         *arena;
+    size_t        arena_bytes;
+    size_t        arena_used;
+    // growable scratch for the kernels themselves (Thomas coefficients, ping-pong fields)
+    char         *scratch;
+    size_t        scratch_bytes;
+    unsigned long long launches;
+    int           kernel_path;     // 0 simple, 1 streaming
+    char          err[512];
+};
+
+int  pdegpu_set_error(pdegpu_ctx *ctx, int status, const char *fmt, ...);
+int  pdegpu_check_cuda(pdegpu_ctx *ctx, cudaError_t e, const char *what);
+// arena: reset at the start of a host-pointer call, bump-allocate 256-B aligned blocks
+int  pdegpu_arena_reserve(pdegpu_ctx *ctx, size_t bytes);     // make sure capacity >= bytes (may realloc; only when empty)
+void pdegpu_arena_reset(pdegpu_ctx *ctx);
+void *pdegpu_arena_alloc(pdegpu_ctx *ctx, size_t bytes);      // nullptr if exhausted
+int  pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes);   // ctx->scratch valid for >= bytes afterwards
+
+#define PDEGPU_CUDA_OK(ctx, call)                                                 \
+    do {                                                                          \
+        cudaError_t e__ = (call);                                                 \
+        if (e__ != cudaSuccess) return pdegpu_check_cuda((ctx), e__, #call);      \
+    } while (0)
+
+#define PDEGPU_LAUNCH_CHECK(ctx, name)                                            \
+    do {                                                                          \
+        (ctx)->launches++;                                                        \
+        cudaError_t e__ = cudaGetLastError();                                     \
+        if (e__ != cudaSuccess) return pdegpu_check_cuda((ctx), e__, name);       \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Device-side view of one system (see pdegpu_system in pdegpu.h)
+// ------------------------------------------------------------------------------------------
+enum { W_W = 0, W_N = 1, W_E = 2, W_S = 3, W_NW = 4, W_NE = 5, W_SE = 6, W_SW = 7 };
+
+struct SysView {
+    float       *x[2];
+    const float *x0[2];
+    const float *m;
+    const float *c[2];
+    const float *d[2];
+    const float *w[8];
+    int          nrows, ncols;
+    long long    bstride;
+};
+
+static inline SysView make_view(const pdegpu_system *s)
+{
+    SysView v;
+    for (int k = 0; k < 2; k++) { v.x[k] = s->x[k]; v.x0[k] = s->x0[k]; v.c[k] = s->c[k]; v.d[k] = s->d[k]; }
+    v.m = s->m;
+    for (int k = 0; k < 8; k++) v.w[k] = s->w[k];
+    v.nrows = s->nrows; v.ncols = s->ncols; v.bstride = s->batch_stride;
+    return v;
+}
+
+__device__ __forceinline__ bool is_nan(float v) { return v != v; }
+
+// family traits
+template <int FAM> struct Fam;
+template <> struct Fam<PDEGPU_FLOW_ELIN4> { static constexpr int NUNK = 2; static constexpr bool LATE = false, EIGHT = false, PDE = false; };
+template <> struct Fam<PDEGPU_FLOW_LLIN4> { static constexpr int NUNK = 2; static constexpr bool LATE = true,  EIGHT = false, PDE = false; };
+template <> struct Fam<PDEGPU_FLOW_LLIN8> { static constexpr int NUNK = 2; static constexpr bool LATE = true,  EIGHT = true,  PDE = false; };
+template <> struct Fam<PDEGPU_DISP_LLIN4> { static constexpr int NUNK = 1; static constexpr bool LATE = true,  EIGHT = false, PDE = false; };
+template <> struct Fam<PDEGPU_PDE4>       { static constexpr int NUNK = 1; static constexpr bool LATE = false, EIGHT = false, PDE = true;  };
+template <> struct Fam<PDEGPU_PDE8>       { static constexpr int NUNK = 1; static constexpr bool LATE = false, EIGHT = true,  PDE = true;  };
+
+// ------------------------------------------------------------------------------------------
+// Kernel launchers implemented in the .cu files (all asynchronous on ctx->stream)
+// ------------------------------------------------------------------------------------------
+int relax_simple(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);
+int relax_stream(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);   // returns PDEGPU_ERR_UNSUPPORTED when it has no kernel for the case
+
+int op_residual(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV, bool lhs);
+int op_llin4_quirks(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV, bool lhs);
+int op_bilin(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y, int nrows, int ncols, int nframes, float oob);
+int op_fst(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
+int op_snd(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
+int op_ddiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS, const float *D, int nrows, int ncols, int nframes, float eps);

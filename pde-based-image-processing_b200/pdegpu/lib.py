@@ -1,0 +1,158 @@
+"""ctypes binding of the libpdegpu C ABI (include/pdegpu.h).
+
+Device memory is addressed by integer pointers (e.g. ``torch.Tensor.data_ptr()``); torch is only
+plumbing for allocation and streams, never part of the compute path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(os.path.dirname(_HERE), "libpdegpu.so")
+
+FLOW_ELIN4, FLOW_LLIN4, FLOW_LLIN8, DISP_LLIN4, PDE4, PDE8 = range(6)
+W_W, W_N, W_E, W_S, W_NW, W_NE, W_SE, W_SW = range(8)
+
+OK = 0
+ERR_NODEVICE = -5
+
+
+class PdegpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpdegpu error {code}: {msg}")
+        self.code = code
+
+
+class System(ctypes.Structure):
+    """Mirror of `pdegpu_system`."""
+    _fields_ = [("family", c_int), ("nrows", c_int), ("ncols", c_int), ("batch", c_int),
+                ("batch_stride", c_longlong),
+                ("x", c_void_p * 2), ("x0", c_void_p * 2), ("m", c_void_p),
+                ("c", c_void_p * 2), ("d", c_void_p * 2), ("w", c_void_p * 8)]
+
+
+_dll = None
+
+
+def dll() -> ctypes.CDLL:
+    global _dll
+    if _dll is None:
+        if not os.path.exists(LIBPATH):
+            raise ImportError(f"{LIBPATH} not built: run `python pde-based-image-processing_b200/build.py` "
+                              "(libpdegpu has no CPU fallback)")
+        L = ctypes.CDLL(LIBPATH)
+        L.pdegpu_device_count.restype = c_int
+        L.pdegpu_init.restype = c_int
+        L.pdegpu_init.argtypes = [c_int, POINTER(c_void_p)]
+        L.pdegpu_free.restype = None
+        L.pdegpu_free.argtypes = [c_void_p]
+        L.pdegpu_last_error.restype = c_char_p
+        L.pdegpu_last_error.argtypes = [c_void_p]
+        L.pdegpu_version.restype = c_char_p
+        L.pdegpu_sync.restype = c_int
+        L.pdegpu_sync.argtypes = [c_void_p]
+        L.pdegpu_stream.restype = c_void_p
+        L.pdegpu_stream.argtypes = [c_void_p]
+        L.pdegpu_launch_count.restype = c_ulonglong
+        L.pdegpu_launch_count.argtypes = [c_void_p]
+        L.pdegpu_set_kernel_path.restype = c_int
+        L.pdegpu_set_kernel_path.argtypes = [c_void_p, c_int]
+        L.pdegpu_dev_relax.restype = c_int
+        L.pdegpu_dev_relax.argtypes = [c_void_p, POINTER(System), c_int, c_float, c_int]
+        L.pdegpu_dev_residual.restype = c_int
+        L.pdegpu_dev_residual.argtypes = [c_void_p, POINTER(System), c_int, c_void_p, c_void_p]
+        L.pdegpu_dev_lhs.restype = c_int
+        L.pdegpu_dev_lhs.argtypes = [c_void_p, POINTER(System), c_int, c_void_p, c_void_p]
+        L.pdegpu_dev_bilin_interp_2d.restype = c_int
+        L.pdegpu_dev_bilin_interp_2d.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 3 + [c_float]
+        L.pdegpu_dev_fst_derivatives5.restype = c_int
+        L.pdegpu_dev_fst_derivatives5.argtypes = [c_void_p] + [c_void_p] * 5 + [c_int] * 3
+        L.pdegpu_dev_snd_derivatives5.restype = c_int
+        L.pdegpu_dev_snd_derivatives5.argtypes = [c_void_p] + [c_void_p] * 7 + [c_int] * 3
+        L.pdegpu_dev_ddiff_weights.restype = c_int
+        L.pdegpu_dev_ddiff_weights.argtypes = [c_void_p] + [c_void_p] * 5 + [c_int] * 3 + [c_float]
+        L.pdegpu_upload.restype = c_int
+        L.pdegpu_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
+        L.pdegpu_download.restype = c_int
+        L.pdegpu_download.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
+        _dll = L
+    return _dll
+
+
+class Context:
+    """One libpdegpu context (= one GPU + one stream). Not thread-safe, like the C object."""
+
+    def __init__(self, device: int = 0):
+        L = dll()
+        h = c_void_p()
+        rc = L.pdegpu_init(device, ctypes.byref(h))
+        if rc != OK:
+            raise PdegpuError(rc, L.pdegpu_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            dll().pdegpu_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise PdegpuError(rc, dll().pdegpu_last_error(self.h).decode())
+
+    @property
+    def stream(self) -> int:
+        return int(dll().pdegpu_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(dll().pdegpu_launch_count(self.h))
+
+    def sync(self):
+        self._chk(dll().pdegpu_sync(self.h))
+
+    def set_kernel_path(self, path: int):
+        self._chk(dll().pdegpu_set_kernel_path(self.h, path))
+
+    def relax(self, sys: System, iters: int, omega: float, solver: int):
+        self._chk(dll().pdegpu_dev_relax(self.h, ctypes.byref(sys), iters, c_float(omega), solver))
+
+    def residual(self, sys: System, nframes: int, RU: int, RV: int):
+        self._chk(dll().pdegpu_dev_residual(self.h, ctypes.byref(sys), nframes, RU, RV))
+
+    def lhs(self, sys: System, nframes: int, AU: int, AV: int):
+        self._chk(dll().pdegpu_dev_lhs(self.h, ctypes.byref(sys), nframes, AU, AV))
+
+    def upload(self, dst_dev: int, src_host: int, nbytes: int):
+        self._chk(dll().pdegpu_upload(self.h, dst_dev, src_host, nbytes))
+
+    def download(self, dst_host: int, src_dev: int, nbytes: int):
+        self._chk(dll().pdegpu_download(self.h, dst_host, src_dev, nbytes))
+
+
+def make_system(family: int, nrows: int, ncols: int, batch: int = 1, batch_stride: int | None = None,
+                x=(), x0=(), m=None, c=(), d=(), w=()) -> System:
+    """Build a `pdegpu_system` from integer device pointers."""
+    s = System()
+    s.family, s.nrows, s.ncols, s.batch = family, nrows, ncols, batch
+    s.batch_stride = nrows * ncols if batch_stride is None else batch_stride
+    for k, p in enumerate(x):
+        s.x[k] = p
+    for k, p in enumerate(x0):
+        s.x0[k] = p
+    s.m = m
+    for k, p in enumerate(c):
+        s.c[k] = p
+    for k, p in enumerate(d):
+        s.d[k] = p
+    for k, p in enumerate(w):
+        s.w[k] = p
+    return s

@@ -1,0 +1,48 @@
+"""Shared fixtures. `-m "not gpu"`: oracle vs reference/golden, ABI, host logic (no GPU needed).
+`-m gpu`: parity of the CUDA path, called through the C ABI / gateways, against the oracle."""
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "pde-based-image-processing_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Make sure libpdegpu + gateways + oracle are built (cross-compiles without a GPU)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pdegpu_build", os.path.join(PKG, "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    if not (os.path.exists(b.LIB) and os.path.exists(b.MEXLIB)):
+        b.build_all()
+    return b
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle.oracle import OracleBackend
+    return OracleBackend()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    from oracle import oracle as o
+    if not o.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return o.RefBackend()
+
+
+@pytest.fixture(scope="session")
+def gpu(built):
+    from pdegpu import mex
+    return mex.GpuBackend()

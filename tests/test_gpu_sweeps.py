@@ -1,0 +1,190 @@
+"""GPU parity, relaxation sweeps.
+
+The reference relaxes in lexicographic order (serial); libpdegpu relaxes the same systems in
+red-black / zebra order. BASELINE.json's bar for that case: agreement AT CONVERGENCE within
+1e-3 px mean end-point error. We run both to convergence on the same system (same boundary
+model, a stable omega) and ask for far less than that; plus order-independent properties at
+the finite iteration counts the drivers use."""
+import numpy as np
+import pytest
+
+from pdegpu import synth
+from util import assert_bitwise, mean_epe, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_EPE = 1e-3          # BASELINE.json north_star, px
+NR, NC = 37, 53
+CONV = {1: (3000, 1.5), 2: (400, 1.3)}       # solver -> (iterations, omega) that reach the fixed point
+
+
+def converged(backend, fn, s, solver, nlhs):
+    it, om = CONV[solver]
+    return backend.call(fn, synth.mex_args(fn, s, it, om, solver), nlhs)
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("fn,late,eight", [("Oflow_sor_elin4_2d", False, False), ("Oflow_sor_llin4_2d", True, False),
+                                           ("Oflow_sor_llin8_2d", True, True)])
+def test_flow_converges_to_reference_fixed_point(gpu, oracle, fn, late, eight, solver):
+    s = synth.flow_system(31, NR, NC, late=late, eight=eight, nan_frac=0.02)
+    g, o = converged(gpu, fn, s, solver, 2), converged(oracle, fn, s, solver, 2)
+    epe = mean_epe(g[0], g[1], o[0], o[1])
+    assert epe < TOL_EPE, epe
+    assert max(rel_err(g[0], o[0]), rel_err(g[1], o[1])) < 2e-3      # in practice ~1e-5
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+def test_disparity_converges_to_reference_fixed_point(gpu, oracle, solver):
+    s = synth.disp_system(32, NR, NC, nan_frac=0.02)
+    g, o = converged(gpu, "Disp_sor_llin4_2d", s, solver, 1), converged(oracle, "Disp_sor_llin4_2d", s, solver, 1)
+    assert float(np.mean(np.abs(g[0] - o[0]))) < TOL_EPE
+    ss = {"f0": synth.disp_system(33, NR, NC), "f1": synth.disp_system(34, NR, NC)}
+    g = converged(gpu, "Disp_sor_llin_sym4_2d", ss, solver, 2)
+    o = converged(oracle, "Disp_sor_llin_sym4_2d", ss, solver, 2)
+    assert mean_epe(g[0], g[1], o[0], o[1]) < TOL_EPE
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("eight", [False, True])
+def test_pde_converges_to_reference_fixed_point(gpu, oracle, eight, solver):
+    fn = "PDEsolver8" if eight else "PDEsolver4"
+    s = synth.pde_system(35, NR, NC, nframes=2, eight=eight, nan_frac=0.02)
+    if eight and solver == 2:
+        # the reference's 8-neighbour ALR runs ONE iteration per call: iterate the call
+        xg, xo = s["X"], s["X"]
+        for _ in range(300):
+            sg, so = dict(s), dict(s)
+            sg["X"], so["X"] = xg, xo
+            xg = gpu.call(fn, synth.mex_args(fn, sg, 4, 1.3, 2), 1)[0]
+            xo = oracle.call(fn, synth.mex_args(fn, so, 4, 1.3, 2), 1)[0]
+        g, o = [xg], [xo]
+    else:
+        g, o = converged(gpu, fn, s, solver, 1), converged(oracle, fn, s, solver, 1)
+    assert float(np.mean(np.abs(g[0] - o[0]))) < TOL_EPE
+    assert rel_err(g[0], o[0]) < 2e-3
+
+
+def test_pde8_line_solver_runs_one_iteration_and_skips_corners(gpu):
+    s = synth.pde_system(36, NR, NC, eight=True)
+    a1 = gpu.call("PDEsolver8", synth.mex_args("PDEsolver8", s, 1, 1.75, 2), 1)[0]
+    a9 = gpu.call("PDEsolver8", synth.mex_args("PDEsolver8", s, 9, 1.75, 2), 1)[0]
+    a0 = gpu.call("PDEsolver8", synth.mex_args("PDEsolver8", s, 0, 1.75, 2), 1)[0]
+    assert_bitwise(a1, a9, "iter ignored")
+    assert_bitwise(a1, a0, "iter ignored (0)")
+    for (i, j) in ((0, 0), (0, NC - 1), (NR - 1, 0), (NR - 1, NC - 1)):
+        assert a1[i, j] == s["X"][i, j]          # corners are never relaxed (pdeSolvers.c:1155,1290)
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+def test_iter_zero_semantics(gpu, solver):
+    s = synth.flow_system(37, NR, NC)
+    u, v = gpu.call("Oflow_sor_elin4_2d", synth.mex_args("Oflow_sor_elin4_2d", s, 0, 1.9, solver), 2)
+    assert not u.any() and not v.any()                       # no memcpy for iter<=0 (Oflow_sor_elin4_2d.c:341)
+    d = synth.disp_system(38, NR, NC)
+    assert not gpu.call("Disp_sor_llin4_2d", synth.mex_args("Disp_sor_llin4_2d", d, 0, 1.9, solver), 1)[0].any()
+    ss = {"f0": d, "f1": synth.disp_system(39, NR, NC)}
+    o = gpu.call("Disp_sor_llin_sym4_2d", synth.mex_args("Disp_sor_llin_sym4_2d", ss, 0, 1.9, solver), 2)
+    assert_bitwise(o[0], ss["f0"]["dU"], "sym copies the guess")  # Disp_sor_llin_sym4_2d.c:418
+    p = synth.pde_system(40, NR, NC)
+    assert_bitwise(gpu.call("PDEsolver4", synth.mex_args("PDEsolver4", p, 0, 1.75, solver), 1)[0], p["X"], "pde4 iter0")
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("shape", [(480, 640), (203, 270), (1080, 1920)])
+def test_residual_drops_at_driver_iteration_counts(gpu, oracle, solver, shape):
+    """Size-independent property at the real sizes: a few sweeps (the drivers' iter=4) must reduce the
+    reference-defined residual, and a further call must reduce it again."""
+    s = synth.flow_system(41, *shape, late=True, nan_frac=0.01)
+    fn = "Oflow_sor_llin4_2d"
+
+    def resnorm(dU, dV):
+        t = dict(s)
+        t["dU"], t["dV"] = dU, dV
+        r = gpu.call(fn, synth.mex_args(fn, t, 0, 1.0, solver), 4)     # GPU residual == oracle residual bitwise (test_gpu_exact)
+        return float(np.sqrt(np.nanmean(r[2].astype(np.float64) ** 2 + r[3].astype(np.float64) ** 2)))
+
+    r0 = resnorm(s["dU"], s["dV"])
+    a = gpu.call(fn, synth.mex_args(fn, s, 4, 1.0, solver), 2)
+    r1 = resnorm(a[0], a[1])
+    t = dict(s)
+    t["dU"], t["dV"] = a
+    b = gpu.call(fn, synth.mex_args(fn, t, 4, 1.0, solver), 2)
+    r2 = resnorm(b[0], b[1])
+    assert r1 < 0.7 * r0 and r2 < r1, (r0, r1, r2)
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+def test_fixed_point_is_stationary(gpu, oracle, solver):
+    """Idempotence: the reference's converged solution is a fixed point of the GPU sweep."""
+    s = synth.flow_system(42, NR, NC, nan_frac=0.02)
+    fn = "Oflow_sor_elin4_2d"
+    o = converged(oracle, fn, s, solver, 2)
+    t = dict(s)
+    t["U"], t["V"] = o
+    g = gpu.call(fn, synth.mex_args(fn, t, 3, 1.2, solver), 2)
+    assert mean_epe(g[0], g[1], o[0], o[1]) < 1e-5
+
+
+@pytest.mark.parametrize("solver", [1, 2])
+@pytest.mark.parametrize("fam", ["elin4", "llin4", "llin8", "disp", "pde4", "pde8"])
+@pytest.mark.parametrize("shape", [(37, 53), (64, 128), (131, 67), (480, 640)])
+def test_kernel_generations_agree(built, fam, solver, shape):
+    """The streaming kernels (generation 1) against the simple global-memory kernels (generation 0):
+    same ordering, same arithmetic -> identical for point sweeps, to rounding for line sweeps."""
+    import torch
+    from pdegpu import lib
+    nr, nc = shape
+    ctx = lib.Context(0)
+    dev = torch.device("cuda:0")
+
+    def up(a):
+        return torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))).to(dev)
+
+    if fam in ("elin4", "llin4", "llin8"):
+        s = synth.flow_system(43, nr, nc, late=fam != "elin4", eight=fam == "llin8")
+        family = {"elin4": lib.FLOW_ELIN4, "llin4": lib.FLOW_LLIN4, "llin8": lib.FLOW_LLIN8}[fam]
+        unk = ("U", "V") if fam == "elin4" else ("dU", "dV")
+        t = {k: up(v) for k, v in s.items()}
+        wk = ("wW", "wN", "wE", "wS") + (("wNW", "wNE", "wSE", "wSW") if fam == "llin8" else ())
+
+        def mk(x0, x1):
+            return lib.make_system(family, nr, nc, x=(x0.data_ptr(), x1.data_ptr()),
+                                   x0=(t["U"].data_ptr(), t["V"].data_ptr()) if fam != "elin4" else (),
+                                   m=t["M"].data_ptr(), c=(t["Cu"].data_ptr(), t["Cv"].data_ptr()),
+                                   d=(t["Du"].data_ptr(), t["Dv"].data_ptr()), w=[t[k].data_ptr() for k in wk])
+        init = [t[unk[0]], t[unk[1]]]
+    elif fam == "disp":
+        s = synth.disp_system(44, nr, nc)
+        t = {k: up(v) for k, v in s.items()}
+
+        def mk(x0, x1):
+            return lib.make_system(lib.DISP_LLIN4, nr, nc, x=(x0.data_ptr(),), x0=(t["U"].data_ptr(),),
+                                   c=(t["Cu"].data_ptr(),), d=(t["Du"].data_ptr(),),
+                                   w=[t[k].data_ptr() for k in ("wW", "wN", "wE", "wS")])
+        init = [t["dU"], t["dU"]]
+    else:
+        eight = fam == "pde8"
+        s = synth.pde_system(45, nr, nc, nframes=3, eight=eight)
+        t = {k: up(v) for k, v in s.items()}
+        wk = ("wW", "wN", "wE", "wS") + (("wNW", "wNE", "wSE", "wSW") if eight else ())
+
+        def mk(x0, x1):
+            return lib.make_system(lib.PDE8 if eight else lib.PDE4, nr, nc, batch=3, x=(x0.data_ptr(),),
+                                   c=(t["B"].data_ptr(),), d=(t["TRACE"].data_ptr(),), w=[t[k].data_ptr() for k in wk])
+        init = [t["X"], t["X"]]
+
+    res = []
+    for path in (0, 1):
+        ctx.set_kernel_path(path)
+        x0, x1 = init[0].clone(), init[1].clone()
+        torch.cuda.synchronize()
+        ctx.relax(mk(x0, x1), 5, 1.9, solver)
+        ctx.sync()
+        res.append((x0.cpu().numpy(), x1.cpu().numpy()))
+    ctx.close()
+    for a, b in zip(res[0], res[1]):
+        if solver == 1:
+            assert_bitwise(a, b, f"{fam} point")
+        else:
+            assert rel_err(a, b) < 2e-5
