@@ -15,11 +15,15 @@ pytestmark = pytest.mark.gpu
 
 TOL_EPE = 1e-3          # BASELINE.json north_star, px
 NR, NC = 37, 53
-CONV = {1: (3000, 1.5), 2: (400, 1.3)}       # solver -> (iterations, omega) that reach the fixed point
+# solver -> (iterations, omega) that reach the fixed point. The reference's point solver couples U and V
+# Jacobi-style inside a pixel (opticalflowSolvers.c:129-152) and DIVERGES for omega >= ~1.3 on these
+# systems (so does the oracle); omega = 1 converges. Scalar systems take omega = 1.5.
+CONV = {1: (800, 1.0), 2: (400, 1.3)}
+CONV_SCALAR = {1: (3000, 1.5), 2: (400, 1.3)}
 
 
 def converged(backend, fn, s, solver, nlhs):
-    it, om = CONV[solver]
+    it, om = (CONV if fn.startswith("Oflow") else CONV_SCALAR)[solver]
     return backend.call(fn, synth.mex_args(fn, s, it, om, solver), nlhs)
 
 
