@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- relaxation-sweep throughput of libpdegpu on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- the inner linear solve of the
+late-linearisation warping flow driver at 640x480: `Oflow_sor_llin4_2d` with the driver's defaults
+(solver 2 = alternating line relaxation, iter = 4, omega = 1.9; reference
+matlab/optical_flow/FlowEminND_llin_2D_v10.m:54-62,332-348) on a batch of independent synthetic
+480x640 systems (structurally valid). The batch is sized so that one pass touches far
+more than the 126 MB L2 (no cache-resident re-use between steps).
+
+One step = one pass of the hot path over the whole batch = batch x iter line-relaxation iterations.
+value = Mpix*iter/s over all ranks, inputs resident in HBM (device pointers, C ABI).
+e2e   = the same metric through the drop-in host-pointer C-ABI call (pdegpu_oflow_sor_llin4_2d),
+        pinned host buffers, H2D + D2H inside the timed region.
+roofline = dominant kernel: algorithmic bytes (60 B/px/sweep for llin4, one ALR iteration
+        = 2 sweeps) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline = the reference's own CPU code (oracle/_ref, compiled unmodified) on the box's host cores.
+
+The oracle/ directory is used here ONLY for the cpu_baseline / --impl reference legs.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "pde-based-image-processing_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+NROWS, NCOLS = 480, 640            # Matlab rows x cols of a 640x480 frame
+ITER, OMEGA, SOLVER = 4, 1.9, 2    # driver defaults
+FN = "Oflow_sor_llin4_2d"
+B1_LLIN4 = 60.0                    # algorithmic bytes / px / sweep
+METRIC = "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, ALR)"
+UNIT = "Mpix*iter/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="independent 480x640 systems per GPU")
+    ap.add_argument("--solver", type=int, default=SOLVER)
+    ap.add_argument("--kernels", default="stream", choices=["stream", "simple"])
+    ap.add_argument("--e2e-calls", type=int, default=4, help="host-pointer calls per e2e step")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU code on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_throughput(seconds_target=10.0, calls_per_worker=None):
+    """Times mex_Oflow_sor_llin4_2d of the unmodified reference (oracle/_ref) on independent 480x640
+    systems, one worker per host core (the reference's sweep is single-threaded; a batch of pairs is
+    embarrassingly parallel, ctypes releases the GIL). Falls back to the C restatement ("port")."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    from pdegpu import synth
+    cores = os.cpu_count() or 1
+    s = synth.flow_system(1235, NROWS, NCOLS, late=True)
+    args = synth.mex_args(FN, s, ITER, OMEGA, SOLVER)
+    kind = "reference" if orc.have_ref() else "port"
+
+    def make_worker():
+        if kind == "reference":
+            # one private copy of the shared object per worker: the mex shim keeps per-library state
+            import shutil
+            import tempfile
+            src = os.path.join(ROOT, "oracle", "_ref", "ref_oflow.so")
+            tmp = tempfile.NamedTemporaryFile(suffix=".so", delete=False)
+            tmp.close()
+            shutil.copy(src, tmp.name)
+            from pdegpu.mex_harness import MexLibrary
+            L = MexLibrary(tmp.name)
+            return lambda: L.call("mex_" + FN, args, 2)
+        be = orc.OracleBackend()
+        return lambda: be.call(FN, args, 2)
+
+    workers = [make_worker() for _ in range(cores)]
+    t0 = time.perf_counter()
+    workers[0]()
+    one = time.perf_counter() - t0
+    n = calls_per_worker or max(1, int(seconds_target / max(one, 1e-3)))
+
+    def run(w):
+        for _ in range(n):
+            w()
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(run, workers))
+    dt = time.perf_counter() - t0
+    units = cores * n * NROWS * NCOLS * ITER / 1e6
+    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{cores} workers x {n} calls of {FN} (480x640, iter={ITER}, omega={OMEGA}, solver={SOLVER}) "
+                      f"= {units:.0f} Mpix*iter in {dt:.1f} s; single-thread rate {NROWS * NCOLS * ITER / 1e6 / one:.2f} {UNIT}"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # W warm-up + K steps, each step a bounded sample
+    cores = os.cpu_count() or 1
+    res, _ = cpu_reference_throughput(seconds_target=1.0)          # warm-up / calibration
+    one_call_s = (NROWS * NCOLS * ITER / 1e6) / (res["value"] / cores)      # per worker
+    per_step_calls = max(1, int(2.0 / max(1e-3, one_call_s)))                   # ~2 s of CPU work per step
+    vals, t_all = [], 0.0
+    for k in range(args.warmup + args.steps):
+        r, dt = cpu_reference_throughput(calls_per_worker=per_step_calls)
+        if k >= args.warmup:
+            vals.append(r["value"])
+            t_all += dt
+    v = float(np.mean(vals))
+    r["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: Oflow_sor_llin4_2d inner solve, 480x640 systems, ALR iter=4 omega=1.9 "
+                               "(reference CPU code, one worker per host core)"},
+        "cpu_baseline": r,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from pdegpu import lib, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = lib.Context(local)
+    ctx.set_kernel_path(1 if args.kernels == "stream" else 0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    B = args.batch
+    n = NROWS * NCOLS
+    # a handful of distinct systems tiled over the batch (generation cost), weak scaling: B per GPU
+    keys = ("U", "V", "dU", "dV", "M", "Cu", "Cv", "Du", "Dv", "wW", "wN", "wE", "wS")
+    base = [synth.flow_system(1235 + 17 * rank + k, NROWS, NCOLS, late=True) for k in range(4)]
+    host = {k: np.stack([base[b % 4][k].reshape(-1, order="F") for b in range(B)]) for k in keys}
+    d = {k: torch.from_numpy(host[k]).to(dev) for k in keys}
+    dU0, dV0 = d["dU"].clone(), d["dV"].clone()
+    sysd = lib.make_system(lib.FLOW_LLIN4, NROWS, NCOLS, batch=B, batch_stride=n,
+                           x=(d["dU"].data_ptr(), d["dV"].data_ptr()), x0=(d["U"].data_ptr(), d["V"].data_ptr()),
+                           m=d["M"].data_ptr(), c=(d["Cu"].data_ptr(), d["Cv"].data_ptr()),
+                           d=(d["Du"].data_ptr(), d["Dv"].data_ptr()),
+                           w=[d[k].data_ptr() for k in ("wW", "wN", "wE", "wS")])
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.relax(sysd, ITER, OMEGA, args.solver)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    # restart from the initial guess so that every measured step does the same work
+    d["dU"].copy_(dU0)
+    d["dV"].copy_(dV0)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ctx.profile(True)
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - l0
+    prof = ctx.profile_report()
+    ctx.profile(False)
+    clocks = sampler.finish() if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units = world * B * n * ITER * args.steps / 1e6
+    value = units / (ms / 1e3)
+
+    # sanity: the batch really was relaxed (finite, changed)
+    assert torch.isfinite(d["dU"]).all() and not torch.equal(d["dU"], dU0)
+
+    # ---- e2e: drop-in host-pointer C-ABI call, pinned host buffers, H2D/D2H inside ----
+    L = lib.dll()
+    L.pdegpu_oflow_sor_llin4_2d.restype = ctypes.c_int
+    L.pdegpu_oflow_sor_llin4_2d.argtypes = [ctypes.c_void_p] * 18 + [ctypes.c_int] * 3 + [ctypes.c_float] * 2 + [ctypes.c_int]
+    pin = {k: torch.from_numpy(base[0][k].reshape(-1, order="F").copy()).pin_memory() for k in keys}
+    out0, out1 = torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def e2e_call():
+        rc = L.pdegpu_oflow_sor_llin4_2d(ctx.h, out0.data_ptr(), out1.data_ptr(), None, None,
+                                         *[pin[k].data_ptr() for k in keys], NROWS, NCOLS, 1,
+                                         float(ITER), float(OMEGA), args.solver)
+        if rc != 0:
+            raise RuntimeError(L.pdegpu_last_error(ctx.h).decode())
+
+    for _ in range(3):
+        e2e_call()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps * args.e2e_calls):
+        e2e_call()                                  # synchronous: returns with the result in host memory
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * e2e_steps * args.e2e_calls * n * ITER / 1e6 / e2e_s
+    assert np.isfinite(out0.numpy()).all()
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        top = max((p for p in prof if p["bytes_total"] > 0), key=lambda p: p["ms_total"], default=None)
+        total_kernel_ms = sum(p["ms_total"] for p in prof) or 1.0
+        roof = None
+        if top:
+            ach = top["bytes_total"] / (top["ms_total"] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                    "launch_ms_avg": top["ms_total"] / top["launches"], "launches": top["launches"],
+                    "share_of_step": top["ms_total"] / total_kernel_ms,
+                    "algorithmic_bytes_per_launch": top["bytes_total"] / top["launches"]}
+        cpu, _ = cpu_reference_throughput(seconds_target=10.0) if world == 1 else (None, 0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"configs[1]: Oflow_sor_llin4_2d inner solve of the 640x480 late-linearisation flow; "
+                                   f"batch of {B} independent 480x640 systems per GPU, iter={ITER}, omega={OMEGA}, solver={args.solver} "
+                                   f"({'zebra line relaxation' if args.solver == 2 else 'red-black point SOR'})",
+                       "batch_per_gpu": B, "nrows": NROWS, "ncols": NCOLS, "iter": ITER, "omega": OMEGA, "solver": args.solver,
+                       "kernels": args.kernels,
+                       "l2": f"inputs larger than L2: {13 * B * n * 4 / 1e6:.0f} MB of fields per pass vs 126 MB L2",
+                       "parallelism": f"batch-parallel x{world}, no data-path collective"},
+            "e2e": {"value": e2e_val, "unit": UNIT,
+                    "h2d_bytes_per_step": 13 * n * 4 * args.e2e_calls, "d2h_bytes_per_step": 2 * n * 4 * args.e2e_calls,
+                    "calls_per_step": args.e2e_calls, "api": "pdegpu_oflow_sor_llin4_2d (host pointers, pinned)"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "kernels": prof,
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -67,6 +67,13 @@ int         pdegpu_sync(pdegpu_ctx *ctx);                    /* wait for the con
 void       *pdegpu_stream(pdegpu_ctx *ctx);                  /* the cudaStream_t, as void*              */
 /* Number of libpdegpu kernels launched through this context since creation (bench evidence). */
 unsigned long long pdegpu_launch_count(const pdegpu_ctx *ctx);
+/* Per-launch timing for benchmarks: while enabled, every kernel launch is bracketed by a CUDA event
+ * pair on the context's stream. pdegpu_profile_report() synchronises and writes a JSON array
+ * [{"kernel","launches","ms_total","bytes_total"}] aggregated by kernel name; bytes_total is the
+ * ALGORITHMIC byte count of those launches, so bytes_total/ms_total is the roofline
+ * figure of that kernel. */
+int         pdegpu_profile_enable(pdegpu_ctx *ctx, int on);
+int         pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen);
 /* Kernel generation: 0 = "simple" global-memory kernels (kept as an in-library cross-check),
  * 1 = streaming register/shared-memory kernels (default). */
 int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);

@@ -66,6 +66,10 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->prof) {
+        for (int k = 0; k < ctx->prof_cap; k++) if (ctx->prof[k].e0) { cudaEventDestroy(ctx->prof[k].e0); cudaEventDestroy(ctx->prof[k].e1); }
+        free(ctx->prof);
+    }
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     cudaStreamDestroy(ctx->stream);
@@ -81,6 +85,66 @@ extern "C" int pdegpu_sync(pdegpu_ctx *ctx)
 
 extern "C" void *pdegpu_stream(pdegpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" unsigned long long pdegpu_launch_count(const pdegpu_ctx *ctx) { return ctx ? ctx->launches : 0ull; }
+
+// ---------------------------------------------------------------------------------------------
+// per-launch profile: event pair around every kernel launch made through PDEGPU_PROF / LAUNCH_CHECK
+// ---------------------------------------------------------------------------------------------
+void pdegpu_prof_begin(pdegpu_ctx *ctx, const char *name, double bytes)
+{
+    if (ctx->prof_n >= ctx->prof_cap) return;
+    pdegpu_prof_rec *r = &ctx->prof[ctx->prof_n];
+    r->name = name;
+    r->bytes = bytes;
+    if (!r->e0) { cudaEventCreate(&r->e0); cudaEventCreate(&r->e1); }
+    cudaEventRecord(r->e0, ctx->stream);
+    ctx->prof_on = 2;      // a record is open
+}
+
+void pdegpu_prof_end(pdegpu_ctx *ctx)
+{
+    if (ctx->prof_on != 2) return;
+    cudaEventRecord(ctx->prof[ctx->prof_n].e1, ctx->stream);
+    ctx->prof_n++;
+    ctx->prof_on = 1;
+}
+
+extern "C" int pdegpu_profile_enable(pdegpu_ctx *ctx, int on)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (on && !ctx->prof) {
+        ctx->prof_cap = 1 << 15;
+        ctx->prof = (pdegpu_prof_rec *)calloc(ctx->prof_cap, sizeof(pdegpu_prof_rec));
+        if (!ctx->prof) { ctx->prof_cap = 0; return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "profile buffer"); }
+    }
+    ctx->prof_n = 0;
+    ctx->prof_on = on ? 1 : 0;
+    return PDEGPU_OK;
+}
+
+// Aggregates the recorded launches by kernel name into a JSON array:
+// [{"kernel": "...", "launches": n, "ms_total": t, "bytes_total": b}, ...]. Synchronises the stream.
+extern "C" int pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen)
+{
+    if (!ctx || !buf || buflen < 3) return PDEGPU_ERR_ARG;
+    PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    struct agg { const char *name; int n; double ms, bytes; } a[64];
+    int na = 0;
+    for (int k = 0; k < ctx->prof_n; k++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof[k].e0, ctx->prof[k].e1) != cudaSuccess) { cudaGetLastError(); continue; }
+        int q = 0;
+        for (; q < na; q++) if (strcmp(a[q].name, ctx->prof[k].name) == 0) break;
+        if (q == na) { if (na == 64) continue; a[na].name = ctx->prof[k].name; a[na].n = 0; a[na].ms = 0; a[na].bytes = 0; na++; }
+        a[q].n++; a[q].ms += ms; a[q].bytes += ctx->prof[k].bytes;
+    }
+    size_t off = 0;
+    off += snprintf(buf + off, buflen - off, "[");
+    for (int q = 0; q < na && off + 200 < buflen; q++)
+        off += snprintf(buf + off, buflen - off, "%s{\"kernel\": \"%s\", \"launches\": %d, \"ms_total\": %.6f, \"bytes_total\": %.0f}",
+                        q ? ", " : "", a[q].name, a[q].n, a[q].ms, a[q].bytes);
+    snprintf(buf + off, buflen - off, "]");
+    return PDEGPU_OK;
+}
 
 extern "C" int pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path)
 {

@@ -25,8 +25,21 @@ struct pdegpu_ctx {
     size_t        scratch_bytes;
     unsigned long long launches;
     int           kernel_path;     // 0 simple, 1 streaming
+    // optional per-launch timing (pdegpu_profile_*): one CUDA event pair per kernel launch
+    int           prof_on;
+    int           prof_n, prof_cap;
+    struct pdegpu_prof_rec *prof;
     char          err[512];
 };
+
+struct pdegpu_prof_rec {
+    const char  *name;
+    double       bytes;            // algorithmic bytes of this launch, 0 if not a roofline kernel
+    cudaEvent_t  e0, e1;
+};
+
+void pdegpu_prof_begin(pdegpu_ctx *ctx, const char *name, double bytes);
+void pdegpu_prof_end(pdegpu_ctx *ctx);
 
 int  pdegpu_set_error(pdegpu_ctx *ctx, int status, const char *fmt, ...);
 int  pdegpu_check_cuda(pdegpu_ctx *ctx, cudaError_t e, const char *what);
@@ -45,9 +58,13 @@ int  pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes);   // ctx->scratch va
 #define PDEGPU_LAUNCH_CHECK(ctx, name)                                            \
     do {                                                                          \
         (ctx)->launches++;                                                        \
+        if ((ctx)->prof_on) pdegpu_prof_end(ctx);                                 \
         cudaError_t e__ = cudaGetLastError();                                     \
         if (e__ != cudaSuccess) return pdegpu_check_cuda((ctx), e__, name);       \
     } while (0)
+
+// put in front of a kernel launch: names it and states its algorithmic bytes for the profile
+#define PDEGPU_PROF(ctx, name, bytes) do { if ((ctx)->prof_on) pdegpu_prof_begin((ctx), (name), (double)(bytes)); } while (0)
 
 // ------------------------------------------------------------------------------------------
 // Device-side view of one system (see pdegpu_system in pdegpu.h)
@@ -85,6 +102,13 @@ template <> struct Fam<PDEGPU_FLOW_LLIN8> { static constexpr int NUNK = 2; stati
 template <> struct Fam<PDEGPU_DISP_LLIN4> { static constexpr int NUNK = 1; static constexpr bool LATE = true,  EIGHT = false, PDE = false; };
 template <> struct Fam<PDEGPU_PDE4>       { static constexpr int NUNK = 1; static constexpr bool LATE = false, EIGHT = false, PDE = true;  };
 template <> struct Fam<PDEGPU_PDE8>       { static constexpr int NUNK = 1; static constexpr bool LATE = false, EIGHT = true,  PDE = true;  };
+
+// algorithmic HBM bytes per pixel per sweep, B1 of SURVEY.md section 8(d): 4 B x (streams read once + written once)
+template <int FAM> constexpr double sweep_bytes()
+{
+    return FAM == PDEGPU_FLOW_ELIN4 ? 52.0 : FAM == PDEGPU_FLOW_LLIN4 ? 60.0 : FAM == PDEGPU_FLOW_LLIN8 ? 76.0
+         : FAM == PDEGPU_DISP_LLIN4 ? 36.0 : FAM == PDEGPU_PDE4 ? 32.0 : 48.0;
+}
 
 // ------------------------------------------------------------------------------------------
 // Kernel launchers implemented in the .cu files (all asynchronous on ctx->stream)

@@ -70,9 +70,11 @@ static int run_point(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float 
     dim3 bgrid((per + 127) / 128, sys->batch);
     for (int it = 0; it < iter; it++) {
         for (int colour = 0; colour < (FOUR ? 4 : 2); colour++) {
+            PDEGPU_PROF(ctx, "rb_point_kernel", sweep_bytes<FAM>() * (double)ni * nj * sys->batch / (FOUR ? 4 : 2));
             rb_point_kernel<FAM><<<grid, block, 0, ctx->stream>>>(v, colour, omega);
             PDEGPU_LAUNCH_CHECK(ctx, "rb_point_kernel");
         }
+        PDEGPU_PROF(ctx, "border_fill_kernel", 0);
         border_fill_kernel<Fam<FAM>::NUNK><<<bgrid, 128, 0, ctx->stream>>>(v);
         PDEGPU_LAUNCH_CHECK(ctx, "border_fill_kernel");
     }
@@ -142,6 +144,8 @@ static int run_line_pass(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system 
     if (rc) return rc;
     float *cp = (float *)ctx->scratch, *dp = cp + (size_t)nslots * n * sys->batch;
     dim3 block(64), grid((nslots + 63) / 64, sys->batch);
+    PDEGPU_PROF(ctx, DIR == 0 ? "zebra_line_kernel<dir0>" : "zebra_line_kernel<dir1>",
+                sweep_bytes<FAM>() * (double)nslots * n * sys->batch / Fam<FAM>::NUNK);
     zebra_line_kernel<FAM, DIR><<<grid, block, 0, ctx->stream>>>(v, colour, q, omega, cp, dp, first, nslots);
     PDEGPU_LAUNCH_CHECK(ctx, "zebra_line_kernel");
     return PDEGPU_OK;

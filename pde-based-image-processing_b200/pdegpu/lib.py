@@ -73,6 +73,10 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_dev_snd_derivatives5.argtypes = [c_void_p] + [c_void_p] * 7 + [c_int] * 3
         L.pdegpu_dev_ddiff_weights.restype = c_int
         L.pdegpu_dev_ddiff_weights.argtypes = [c_void_p] + [c_void_p] * 5 + [c_int] * 3 + [c_float]
+        L.pdegpu_profile_enable.restype = c_int
+        L.pdegpu_profile_enable.argtypes = [c_void_p, c_int]
+        L.pdegpu_profile_report.restype = c_int
+        L.pdegpu_profile_report.argtypes = [c_void_p, c_char_p, c_size_t]
         L.pdegpu_upload.restype = c_int
         L.pdegpu_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
         L.pdegpu_download.restype = c_int
@@ -121,6 +125,15 @@ class Context:
 
     def set_kernel_path(self, path: int):
         self._chk(dll().pdegpu_set_kernel_path(self.h, path))
+
+    def profile(self, on: bool):
+        self._chk(dll().pdegpu_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self):
+        import json
+        buf = ctypes.create_string_buffer(1 << 16)
+        self._chk(dll().pdegpu_profile_report(self.h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     def relax(self, sys: System, iters: int, omega: float, solver: int):
         self._chk(dll().pdegpu_dev_relax(self.h, ctypes.byref(sys), iters, c_float(omega), solver))
