@@ -19,8 +19,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 GW = os.path.join(HERE, "gateways")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libpdegpu.so")
+OBJ = os.path.join(HERE, "build" + os.environ.get("PDEGPU_BUILD_SUFFIX", ""))
+LIB = os.path.join(HERE, os.environ.get("PDEGPU_BUILD_NAME", "libpdegpu.so"))
 MEXLIB = os.path.join(GW, "pdegpu_mex.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -61,7 +61,7 @@ def build_lib(force=False, verbose=False):
         objs.append(o)
         if force or not _newer(o, [s] + hdrs):
             extra = ["-Xptxas", "-v"] if verbose else []
-            jobs.append([NVCC] + NVCC_FLAGS + extra + ["-c", s, "-o", o])
+            jobs.append([NVCC] + NVCC_FLAGS + extra + os.environ.get("PDEGPU_NVCC_EXTRA", "").split() + ["-c", s, "-o", o])
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         outs = list(ex.map(_run, jobs))
     if verbose:

@@ -20,6 +20,7 @@
 // HBM traffic per launch = every coefficient of the active lines once + the unknowns of the active
 // lines and of their perpendicular neighbours once + one write of the active lines.
 #include "stencil_math.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -29,81 +30,113 @@ template <int NUNK> struct Slots;
 template <> struct Slots<2> { enum { A = 0, C = 1, B1 = 2, D1 = 3, B2 = 4, D2 = 5, M = 6, GP = 7, XO = 8, N = 9 }; };
 template <> struct Slots<1> { enum { A = 0, C = 1, B1 = 2, D1 = 3, GP = 4, XO = 5, B2 = 2, D2 = 3, M = 0, N = 6 }; };
 
-// Tridiagonal rows of all unknowns at pixel (i,j) for a line along DIR; `qa` is the unknown solved
-// first. d[qa] is complete (coupling taken with the other unknown's current value); d[qb] lacks the
-// coupling term, which is m * x_qa(new) and is added by the solver.
+// Raw operands of one pixel's tridiagonal rows. load() issues every global load unconditionally
+// (neighbours that do not exist are redirected to the pixel itself), so that a thread can have the
+// loads of several pixels in flight before it touches any of them: phase A is latency-bound otherwise.
 template <int FAM, int DIR>
-__device__ __forceinline__ void assemble(const SysView &s, long long pos, int i, int j,
-                                         float &a, float &c, float (&b)[2], float (&d)[2], float &m)
-{
+struct PixelRaw {
     using F = Fam<FAM>;
-    constexpr int NN = F::EIGHT ? 8 : 4;
-    constexpr int prev = DIR == 0 ? W_N : W_W, next = DIR == 0 ? W_S : W_E;
-    constexpr int qa = (F::NUNK == 2 && DIR == 1) ? 1 : 0, qb = 1 - qa;
-    const int nr = s.nrows, nc = s.ncols;
-    const bool eN = i > 0, eS = i < nr - 1, eW = j > 0, eE = j < nc - 1;
-    const bool ex[8] = {eW, eN, eE, eS, eN && eW, eN && eE, eS && eE, eS && eW};
-    const long long off[8] = {-(long long)nr, -1, (long long)nr, 1, -(long long)nr - 1, (long long)nr - 1, (long long)nr + 1, -(long long)nr + 1};
+    static constexpr int NN = F::EIGHT ? 8 : 4;
+    static constexpr int prev = DIR == 0 ? W_N : W_W, next = DIR == 0 ? W_S : W_E;
+    static constexpr int qa = (F::NUNK == 2 && DIR == 1) ? 1 : 0, qb = 1 - qa;
     float w[NN];
+    float xn[F::NUNK][NN];      // unknowns at the perpendicular neighbours
+    float x0n[F::LATE ? F::NUNK : 1][NN], x0c[F::LATE ? F::NUNK : 1];
+    float C[F::NUNK], D[F::NUNK], xo[F::NUNK], M;
+    unsigned exmask;
+
+    // `ip` = pixel index inside the problem (int), pointers in `s` already point at the problem.
+    __device__ __forceinline__ void load(const SysView &s, int ip, int i, int j)
+    {
+        const int nr = s.nrows, nc = s.ncols;
+        const bool eN = i > 0, eS = i < nr - 1, eW = j > 0, eE = j < nc - 1;
+        const bool ex[8] = {eW, eN, eE, eS, eN && eW, eN && eE, eS && eE, eS && eW};
+        const int off[8] = {-nr, -1, nr, 1, -nr - 1, nr - 1, nr + 1, -nr + 1};
+        exmask = 0;
 #pragma unroll
-    for (int n = 0; n < NN; n++) w[n] = s.w[n][pos];
-    a = ex[prev] ? -w[prev] : 0.0f;
-    c = ex[next] ? -w[next] : 0.0f;
-    float bsum = 0.0f, dsum[2] = {0.0f, 0.0f};
-    float x0c[2] = {0.0f, 0.0f};
-    if (F::LATE) {
+        for (int n = 0; n < NN; n++) {
+            exmask |= ex[n] ? (1u << n) : 0u;
+            const int pn = ex[n] ? ip + off[n] : ip;
+            w[n] = s.w[n][ip];
+            const bool inl = (n == prev) || (n == next);
 #pragma unroll
-        for (int q = 0; q < F::NUNK; q++) x0c[q] = s.x0[q][pos];
-    }
-#pragma unroll
-    for (int n = 0; n < NN; n++) {
-        if (!ex[n]) continue;
-        bsum += w[n];
-        const bool inl = (n == prev) || (n == next);
+            for (int q = 0; q < F::NUNK; q++) {
+                if (!inl) xn[q][n] = s.x[q][pn];
+                if (F::LATE) x0n[q][n] = s.x0[q][pn];
+            }
+        }
 #pragma unroll
         for (int q = 0; q < F::NUNK; q++) {
-            if (F::LATE) {
-                float t = s.x0[q][pos + off[n]] - x0c[q];
-                if (!inl) t += s.x[q][pos + off[n]];
-                dsum[q] += w[n] * t;
-            } else if (!inl) {
-                dsum[q] += w[n] * s.x[q][pos + off[n]];
-            }
+            if (F::LATE) x0c[q] = s.x0[q][ip];
+            C[q] = s.c[q][ip];
+            D[q] = s.d[q][ip];
+            xo[q] = s.x[q][ip];
         }
+        M = (F::NUNK == 2) ? s.m[ip] : 0.0f;
     }
-    m = 0.0f;
-    b[1] = 1.0f; d[1] = 0.0f;
-    if (F::PDE) {
-        const float tr = s.d[0][pos];
-        if (!is_nan(tr)) { b[0] = tr; d[0] = dsum[0] + s.c[0][pos]; }
-        else {
-            if (F::EIGHT)   // pdeSolvers.c:1179: wNW twice, wNE never
-                b[0] = (s.w[W_N][pos] + s.w[W_S][pos] + s.w[W_W][pos] + s.w[W_E][pos])
-                     + (s.w[W_NW][pos] + s.w[W_NW][pos] + s.w[W_SW][pos] + s.w[W_SE][pos]);
-            else b[0] = bsum;
-            d[0] = dsum[0];
-        }
-        return;
-    }
+
+    // a,c: sub/super diagonal; b[q],d[q]: diagonal and right-hand side of unknown q. d[qa] is complete
+    // (coupling taken with the other unknown's current value); d[qb] lacks the coupling term, which is
+    // m * x_qa(new) and is added by the solver.
+    __device__ __forceinline__ void rows(float &a, float &c, float (&b)[2], float (&d)[2], float &m) const
+    {
+        a = (exmask >> prev) & 1 ? -w[prev] : 0.0f;
+        c = (exmask >> next) & 1 ? -w[next] : 0.0f;
+        float bsum = 0.0f, dsum[2] = {0.0f, 0.0f};
 #pragma unroll
-    for (int q = 0; q < F::NUNK; q++) {
-        const float C = s.c[q][pos];
-        b[q] = bsum; d[q] = dsum[q];
-        if (!is_nan(C)) {
-            b[q] += s.d[q][pos];
-            d[q] += C;
-            if (F::NUNK == 2) {
-                const float M = s.m[pos];
-                if (q == qa) d[q] -= M * s.x[qb][pos];
-                else m = M;
+        for (int n = 0; n < NN; n++) {
+            const bool e = (exmask >> n) & 1;
+            const bool inl = (n == prev) || (n == next);
+            bsum += e ? w[n] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < F::NUNK; q++) {
+                float t = 0.0f;
+                if (F::LATE) t = x0n[q][n] - x0c[q];
+                if (!inl) t += xn[q][n];
+                if (F::LATE || !inl) dsum[q] += e ? w[n] * t : 0.0f;
+            }
+        }
+        m = 0.0f;
+        b[1] = 1.0f; d[1] = 0.0f;
+        if (F::PDE) {
+            if (!is_nan(D[0])) { b[0] = D[0]; d[0] = dsum[0] + C[0]; }
+            else {
+                if (F::EIGHT)   // pdeSolvers.c:1179: wNW twice, wNE never
+                    b[0] = (w[W_N] + w[W_S] + w[W_W] + w[W_E]) + (w[W_NW % NN] + w[W_NW % NN] + w[W_SW % NN] + w[W_SE % NN]);
+                else b[0] = bsum;
+                d[0] = dsum[0];
+            }
+            return;
+        }
+#pragma unroll
+        for (int q = 0; q < F::NUNK; q++) {
+            b[q] = bsum; d[q] = dsum[q];
+            if (!is_nan(C[q])) {
+                b[q] += D[q];
+                d[q] += C[q];
+                if (F::NUNK == 2) {
+                    if (q == qa) d[q] -= M * xo[qb];
+                    else m = M;
+                }
             }
         }
     }
-}
+};
 
 // ---- phase B: one warp solves one line held in shared memory -------------------------------
+// 1/x to 1 ulp (MUFU.RCP). The sweeps only have to reach the reference's fixed point, and a relaxation
+// step is a contraction, so a 1-ulp reciprocal changes nothing that can be observed; it shortens the
+// serial dependency chain of the elimination from ~80 to ~25 cycles per row.
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Solves a_k x_{k-1} + b_k x_k + c_k x_{k+1} = d_k (- mm_k * y_k when COUPLED), k = 0..n-1, in place:
 // on return D[k] holds omega*x_k + (1-omega)*XO[k] (RELAX) or x_k. B and GP are clobbered.
+// Every loop loads row r+1 before it works on row r (the recurrences are latency chains).
 template <bool COUPLED, bool RELAX>
 __device__ __forceinline__ void warp_line_solve(const float *__restrict__ A, const float *__restrict__ Cc,
                                                 float *__restrict__ B, float *__restrict__ D, float *__restrict__ GP,
@@ -117,15 +150,21 @@ __device__ __forceinline__ void warp_line_solve(const float *__restrict__ A, con
     const int o = lane * Lp;                      // padded smem offset of this lane's chunk
     float cp = 0.f, dp = 0.f, gp = 0.f;
     // pass 1: local forward elimination, spike column gp multiplies x_{s0-1}
-    for (int r = 0; r < len; r++) {
-        const float a = A[o + r], b = B[o + r], c = Cc[o + r];
-        float d = D[o + r];
-        if (COUPLED) d -= MM[o + r] * Y[o + r];
-        float inv, ng;
-        if (r == 0) { inv = 1.0f / b; dp = d * inv; ng = a * inv; }
-        else        { inv = 1.0f / (b - a * cp); dp = (d - a * dp) * inv; ng = -a * gp * inv; }
-        cp = c * inv; gp = ng;
-        B[o + r] = cp; D[o + r] = dp; GP[o + r] = gp;
+    if (len > 0) {
+        float an = A[o], bn = B[o], cn = Cc[o], dn = D[o];
+        if (COUPLED) dn -= MM[o] * Y[o];
+        for (int r = 0; r < len; r++) {
+            const float a = an, b = bn, c = cn, d = dn;
+            if (r + 1 < len) {
+                an = A[o + r + 1]; bn = B[o + r + 1]; cn = Cc[o + r + 1]; dn = D[o + r + 1];
+                if (COUPLED) dn -= MM[o + r + 1] * Y[o + r + 1];
+            }
+            const float inv = fast_rcp(r == 0 ? b : b - a * cp);
+            dp = (r == 0 ? d : d - a * dp) * inv;
+            gp = (r == 0 ? a : -a * gp) * inv;
+            cp = c * inv;
+            B[o + r] = cp; D[o + r] = dp; GP[o + r] = gp;
+        }
     }
     // last-row relation of the chunk:  x_t + cp*x_{t+1} + gp*x_{s0-1} = dp
     // pass 2: first-row relation  x_s = Af - Bf*x_t - Gf*x_{s0-1}
@@ -133,11 +172,15 @@ __device__ __forceinline__ void warp_line_solve(const float *__restrict__ A, con
     if (len == 1) Bf = -1.0f;
     else if (len >= 2) {
         Af = D[o + len - 2]; Bf = B[o + len - 2]; Gf = GP[o + len - 2];
-        for (int r = len - 3; r >= 0; r--) {
-            const float cpr = B[o + r];
-            Af = D[o + r] - cpr * Af;
-            Bf = -cpr * Bf;
-            Gf = GP[o + r] - cpr * Gf;
+        if (len >= 3) {
+            float cn = B[o + len - 3], dn = D[o + len - 3], gn = GP[o + len - 3];
+            for (int r = len - 3; r >= 0; r--) {
+                const float cpr = cn, dpr = dn, gpr = gn;
+                if (r > 0) { cn = B[o + r - 1]; dn = D[o + r - 1]; gn = GP[o + r - 1]; }
+                Af = dpr - cpr * Af;
+                Bf = -cpr * Bf;
+                Gf = gpr - cpr * Gf;
+            }
         }
     }
     // interface system in the chunks' last unknowns l: al*l[-1] + be*l + ga*l[+1] = de
@@ -155,109 +198,157 @@ __device__ __forceinline__ void warp_line_solve(const float *__restrict__ A, con
         float gap = __shfl_down_sync(FULL, ga, st), dep = __shfl_down_sync(FULL, de, st);
         if (lane < st)       { alm = 0.f; bem = 1.0f; gam = 0.f; dem = 0.f; }
         if (lane + st > 31)  { alp = 0.f; bep = 1.0f; gap = 0.f; dep = 0.f; }
-        const float k1 = al / bem, k2 = ga / bep;
+        const float k1 = al * fast_rcp(bem), k2 = ga * fast_rcp(bep);
         be = be - gam * k1 - alp * k2;
         de = de - dem * k1 - dep * k2;
         al = -alm * k1;
         ga = -gap * k2;
     }
-    const float l = de / be;
+    const float l = de * fast_rcp(be);
     float L = __shfl_up_sync(FULL, l, 1);
     if (lane == 0) L = 0.f;
     // pass 3: local back substitution
-    float x = l;
-    for (int r = len - 1; r >= 0; r--) {
-        if (r < len - 1) x = D[o + r] - B[o + r] * x - GP[o + r] * L;
-        D[o + r] = RELAX ? omega * x + (1.0f - omega) * XO[o + r] : x;
+    if (len > 0) {
+        float x = l;
+        float xo = RELAX ? XO[o + len - 1] : 0.f;
+        float cn = 0.f, dn = 0.f, gn = 0.f, xon = 0.f;
+        if (len >= 2) { cn = B[o + len - 2]; dn = D[o + len - 2]; gn = GP[o + len - 2]; if (RELAX) xon = XO[o + len - 2]; }
+        D[o + len - 1] = RELAX ? omega * x + (1.0f - omega) * xo : x;
+        for (int r = len - 2; r >= 0; r--) {
+            const float cpr = cn, dpr = dn, gpr = gn, xor_ = xon;
+            if (r > 0) { cn = B[o + r - 1]; dn = D[o + r - 1]; gn = GP[o + r - 1]; if (RELAX) xon = XO[o + r - 1]; }
+            x = dpr - cpr * x - gpr * L;
+            D[o + r] = RELAX ? omega * x + (1.0f - omega) * xor_ : x;
+        }
     }
 }
 
-template <int FAM, int DIR, int G>
-__global__ void __launch_bounds__(32 * G)
-alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int Lc, int Lp)
+template <int FAM, int DIR, int G, int TPL>      // G lines per CTA, TPL threads per line (>= 32)
+__global__ void __launch_bounds__(TPL * G)
+alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int Lc, int Lp, int dbg)
 {
     using F = Fam<FAM>;
     using S = Slots<F::NUNK>;
     extern __shared__ float smem[];
     constexpr int qa = (F::NUNK == 2 && DIR == 1) ? 1 : 0, qb = 1 - qa;
+    constexpr int NT = TPL * G;
     const int nr = s.nrows, nc = s.ncols;
     const int n = DIR == 0 ? nr : nc;
     const int NP = 32 * Lp;                                  // padded line length
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot0 = blockIdx.x * G;                        // first line slot of this CTA
-    const long long base = (long long)blockIdx.y * s.bstride;
     const int nl = min(G, nslots - slot0);                   // lines really present
+    // move every pointer to this CTA's problem once; pixel indices are plain ints from here on
+    {
+        const long long base = (long long)blockIdx.y * s.bstride;
+#pragma unroll
+        for (int q = 0; q < F::NUNK; q++) { s.x[q] += base; s.c[q] += base; s.d[q] += base; if (F::LATE) s.x0[q] += base; }
+        if (F::NUNK == 2) s.m += base;
+#pragma unroll
+        for (int q = 0; q < (F::EIGHT ? 8 : 4); q++) s.w[q] += base;
+    }
+    // thread -> (line g, first position k0, stride) in memory-friendly order:
+    //   DIR 0: consecutive threads walk consecutive i of one column (128-B rows);
+    //   DIR 1: consecutive threads take the CTA's G neighbouring lines at one j (one sector), then the next j.
+    const int g = DIR == 0 ? tid / TPL : tid % G;
+    const int kfirst = DIR == 0 ? tid % TPL : tid / G;
+    constexpr int KSTEP = TPL;
+    const int line = first_line + colour + 2 * (slot0 + g);
+    const bool active = g < nl;
+    float *Ls = smem + (size_t)g * S::N * NP;
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Lc - 1) / (unsigned)Lc);   // k / Lc == umulhi(k, magic) for k, Lc < 65536
 
     // ---- phase A ----
-    const int total = nl * n;
-    for (int t = tid; t < total; t += 32 * G) {
-        int g, k;
-        if (DIR == 0) { g = t / n; k = t - g * n; }          // k (= i) fastest: 128-B rows of a column
-        else          { k = t / nl; g = t - k * nl; }        // line (= i) fastest: one sector per j
-        const int line = first_line + colour + 2 * (slot0 + g);
-        const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
-        const long long pos = base + (long long)j * nr + i;
-        float a, c, b[2], d[2], m;
-        assemble<FAM, DIR>(s, pos, i, j, a, c, b, d, m);
-        const int ad = (k / Lc) * Lp + (k % Lc);
-        float *Ls = smem + (size_t)g * S::N * NP;
-        Ls[S::A * NP + ad] = a;
-        Ls[S::C * NP + ad] = c;
-        Ls[S::B1 * NP + ad] = b[qa];
-        Ls[S::D1 * NP + ad] = d[qa];
-        Ls[S::XO * NP + ad] = s.x[qa][pos];
-        if (F::NUNK == 2) {
-            Ls[S::B2 * NP + ad] = b[qb];
-            Ls[S::D2 * NP + ad] = d[qb];
-            Ls[S::M * NP + ad] = m;
+#ifndef PDEGPU_ALR_UNR
+#define PDEGPU_ALR_UNR 2
+#endif
+    constexpr int UNR = PDEGPU_ALR_UNR;                      // pixels in flight per thread
+    if (active && !(dbg & 2)) {
+        for (int k0 = kfirst; k0 < n; k0 += UNR * KSTEP) {
+            PixelRaw<FAM, DIR> raw[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int k = min(k0 + u * KSTEP, n - 1);    // tail: recompute the last pixel, harmless
+                const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
+                raw[u].load(s, j * nr + i, i, j);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+                const int k = min(k0 + u * KSTEP, n - 1);
+                const int ch = (int)__umulhi((unsigned)k, magic);
+                const int ad = ch * Lp + (k - ch * Lc);
+                float a, c, b[2], d[2], m;
+                raw[u].rows(a, c, b, d, m);
+                Ls[S::A * NP + ad] = a;
+                Ls[S::C * NP + ad] = c;
+                Ls[S::B1 * NP + ad] = b[qa];
+                Ls[S::D1 * NP + ad] = d[qa];
+                Ls[S::XO * NP + ad] = raw[u].xo[qa];
+                if (F::NUNK == 2) {
+                    Ls[S::B2 * NP + ad] = b[qb];
+                    Ls[S::D2 * NP + ad] = d[qb];
+                    Ls[S::M * NP + ad] = m;
+                }
+            }
+        }
+    }
+    if (dbg & 2) {                                           // probe: benign constant systems instead of phase A
+        for (int t = tid; t < G * S::N * NP; t += NT) smem[t] = 1.0f;
+        __syncthreads();
+        for (int t = tid; t < G * NP; t += NT) {
+            const int gq = t / NP, ad = t - gq * NP;
+            float *Lq = smem + (size_t)gq * S::N * NP;
+            Lq[S::A * NP + ad] = -1.0f; Lq[S::C * NP + ad] = -1.0f; Lq[S::B1 * NP + ad] = 4.0f;
+            if (F::NUNK == 2) { Lq[S::B2 * NP + ad] = 4.0f; Lq[S::M * NP + ad] = 0.1f; }
         }
     }
     __syncthreads();
 
     // ---- phase B ----
-    if (warp < nl) {
-        float *Ls = smem + (size_t)warp * S::N * NP;
-        warp_line_solve<false, true>(Ls + S::A * NP, Ls + S::C * NP, Ls + S::B1 * NP, Ls + S::D1 * NP, Ls + S::GP * NP,
-                                     nullptr, nullptr, Ls + S::XO * NP, n, Lc, Lp, omega, lane);
+    if (warp < nl && !(dbg & 1)) {
+        float *Lw = smem + (size_t)warp * S::N * NP;
+        warp_line_solve<false, true>(Lw + S::A * NP, Lw + S::C * NP, Lw + S::B1 * NP, Lw + S::D1 * NP, Lw + S::GP * NP,
+                                     nullptr, nullptr, Lw + S::XO * NP, n, Lc, Lp, omega, lane);
         if (F::NUNK == 2) {
             __syncwarp();
-            warp_line_solve<true, false>(Ls + S::A * NP, Ls + S::C * NP, Ls + S::B2 * NP, Ls + S::D2 * NP, Ls + S::GP * NP,
-                                         Ls + S::M * NP, Ls + S::D1 * NP, nullptr, n, Lc, Lp, omega, lane);
+            warp_line_solve<true, false>(Lw + S::A * NP, Lw + S::C * NP, Lw + S::B2 * NP, Lw + S::D2 * NP, Lw + S::GP * NP,
+                                         Lw + S::M * NP, Lw + S::D1 * NP, nullptr, n, Lc, Lp, omega, lane);
         }
     }
     __syncthreads();
 
     // ---- phase C ----
-    for (int t = tid; t < total; t += 32 * G) {
-        int g, k;
-        if (DIR == 0) { g = t / n; k = t - g * n; }
-        else          { k = t / nl; g = t - k * nl; }
-        const int line = first_line + colour + 2 * (slot0 + g);
-        const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
-        const long long pos = base + (long long)j * nr + i;
-        const int ad = (k / Lc) * Lp + (k % Lc);
-        const float *Ls = smem + (size_t)g * S::N * NP;
-        s.x[qa][pos] = Ls[S::D1 * NP + ad];
-        if (F::NUNK == 2) {
-            float *X2 = s.x[qb];
-            X2[pos] = omega * Ls[S::D2 * NP + ad] + (1.0f - omega) * X2[pos];
+    if (active && !(dbg & 4)) {
+        for (int k = kfirst; k < n; k += KSTEP) {
+            const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
+            const int ip = j * nr + i;
+            const int ch = (int)__umulhi((unsigned)k, magic);
+            const int ad = ch * Lp + (k - ch * Lc);
+            s.x[qa][ip] = Ls[S::D1 * NP + ad];
+            if (F::NUNK == 2) {
+                float *X2 = s.x[qb];
+                X2[ip] = omega * Ls[S::D2 * NP + ad] + (1.0f - omega) * X2[ip];
+            }
         }
     }
 }
 
-template <int FAM, int DIR, int G>
+#ifndef PDEGPU_ALR_TPL
+#define PDEGPU_ALR_TPL 64
+#endif
+template <int FAM, int DIR, int G, int TPL = (G >= 8 ? 32 : PDEGPU_ALR_TPL)>
 int launch_alr(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int colour, float omega,
                int first, int nslots, int n, int Lc, int Lp, size_t smem)
 {
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_kernel<FAM, DIR, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        cudaError_t e = cudaFuncSetAttribute(alr_kernel<FAM, DIR, G, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_kernel)");
         attr_set[ctx->device & 15] = true;
     }
     dim3 grid((nslots + G - 1) / G, sys->batch);
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_kernel<dir0>" : "alr_kernel<dir1>", sweep_bytes<FAM>() * (double)nslots * n * sys->batch);
-    alr_kernel<FAM, DIR, G><<<grid, 32 * G, smem, ctx->stream>>>(v, colour, omega, first, nslots, Lc, Lp);
+    alr_kernel<FAM, DIR, G, TPL><<<grid, TPL * G, smem, ctx->stream>>>(v, colour, omega, first, nslots, Lc, Lp, getenv("PDEGPU_DBG") ? atoi(getenv("PDEGPU_DBG")) : 0);
     PDEGPU_LAUNCH_CHECK(ctx, "alr_kernel");
     return PDEGPU_OK;
 }
@@ -295,6 +386,7 @@ int alr_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     SysView v = make_view(sys);
     if (Fam<FAM>::PDE && Fam<FAM>::EIGHT) iter = 1;            // pdeSolvers.c:362
     // refuse up front (before touching the unknowns) if either direction does not fit
+    if ((long long)sys->nrows * sys->ncols >= (1ll << 31) || sys->nrows >= 65536 || sys->ncols >= 65536) return PDEGPU_ERR_UNSUPPORTED;
     {
         const size_t per = (size_t)Slots<Fam<FAM>::NUNK>::N * 32 * sizeof(float);
         const int L0 = ((sys->nrows + 31) / 32) | 1, L1 = ((sys->ncols + 31) / 32) | 1;

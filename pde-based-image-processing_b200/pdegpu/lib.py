@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(os.path.dirname(_HERE), "libpdegpu.so")
+LIBPATH = os.environ.get("PDEGPU_LIB") or os.path.join(os.path.dirname(_HERE), "libpdegpu.so")
 
 FLOW_ELIN4, FLOW_LLIN4, FLOW_LLIN8, DISP_LLIN4, PDE4, PDE8 = range(6)
 W_W, W_N, W_E, W_S, W_NW, W_NE, W_SE, W_SW = range(8)
