@@ -33,12 +33,14 @@ template <> struct Slots<1> { enum { A = 0, C = 1, B1 = 2, D1 = 3, GP = 4, XO = 
 // Raw operands of one pixel's tridiagonal rows. load() issues every global load unconditionally
 // (neighbours that do not exist are redirected to the pixel itself), so that a thread can have the
 // loads of several pixels in flight before it touches any of them: phase A is latency-bound otherwise.
+// DIR: 0 = lines along i, first unknown first; 1 = lines along j, second unknown first (the reference's
+// row pass); 2 = a row pass executed as lines along i of the TRANSPOSED problem (see alr_run).
 template <int FAM, int DIR>
 struct PixelRaw {
     using F = Fam<FAM>;
     static constexpr int NN = F::EIGHT ? 8 : 4;
-    static constexpr int prev = DIR == 0 ? W_N : W_W, next = DIR == 0 ? W_S : W_E;
-    static constexpr int qa = (F::NUNK == 2 && DIR == 1) ? 1 : 0, qb = 1 - qa;
+    static constexpr int prev = (DIR & 1) == 0 ? W_N : W_W, next = (DIR & 1) == 0 ? W_S : W_E;
+    static constexpr int qa = (F::NUNK == 2 && DIR != 0) ? 1 : 0, qb = 1 - qa;
     float w[NN];
     float xn[F::NUNK][NN];      // unknowns at the perpendicular neighbours
     float x0n[F::LATE ? F::NUNK : 1][NN], x0c[F::LATE ? F::NUNK : 1];
@@ -101,8 +103,9 @@ struct PixelRaw {
         if (F::PDE) {
             if (!is_nan(D[0])) { b[0] = D[0]; d[0] = dsum[0] + C[0]; }
             else {
-                if (F::EIGHT)   // pdeSolvers.c:1179: wNW twice, wNE never
-                    b[0] = (w[W_N] + w[W_S] + w[W_W] + w[W_E]) + (w[W_NW % NN] + w[W_NW % NN] + w[W_SW % NN] + w[W_SE % NN]);
+                if (F::EIGHT)   // pdeSolvers.c:1179: wNW twice, wNE never (on a transposed problem SW <-> NE)
+                    b[0] = (w[W_N] + w[W_S] + w[W_W] + w[W_E])
+                         + (w[W_NW % NN] + w[W_NW % NN] + w[(DIR == 2 ? W_NE : W_SW) % NN] + w[W_SE % NN]);
                 else b[0] = bsum;
                 d[0] = dsum[0];
             }
@@ -230,10 +233,10 @@ alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int L
     using F = Fam<FAM>;
     using S = Slots<F::NUNK>;
     extern __shared__ float smem[];
-    constexpr int qa = (F::NUNK == 2 && DIR == 1) ? 1 : 0, qb = 1 - qa;
+    constexpr int qa = (F::NUNK == 2 && DIR != 0) ? 1 : 0, qb = 1 - qa;
     constexpr int NT = TPL * G;
     const int nr = s.nrows, nc = s.ncols;
-    const int n = DIR == 0 ? nr : nc;
+    const int n = (DIR & 1) == 0 ? nr : nc;
     const int NP = 32 * Lp;                                  // padded line length
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot0 = blockIdx.x * G;                        // first line slot of this CTA
@@ -250,8 +253,8 @@ alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int L
     // thread -> (line g, first position k0, stride) in memory-friendly order:
     //   DIR 0: consecutive threads walk consecutive i of one column (128-B rows);
     //   DIR 1: consecutive threads take the CTA's G neighbouring lines at one j (one sector), then the next j.
-    const int g = DIR == 0 ? tid / TPL : tid % G;
-    const int kfirst = DIR == 0 ? tid % TPL : tid / G;
+    const int g = (DIR & 1) == 0 ? tid / TPL : tid % G;
+    const int kfirst = (DIR & 1) == 0 ? tid % TPL : tid / G;
     constexpr int KSTEP = TPL;
     const int line = first_line + colour + 2 * (slot0 + g);
     const bool active = g < nl;
@@ -269,7 +272,7 @@ alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int L
 #pragma unroll
             for (int u = 0; u < UNR; u++) {
                 const int k = min(k0 + u * KSTEP, n - 1);    // tail: recompute the last pixel, harmless
-                const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
+                const int i = (DIR & 1) == 0 ? k : line, j = (DIR & 1) == 0 ? line : k;
                 raw[u].load(s, j * nr + i, i, j);
             }
 #pragma unroll
@@ -320,7 +323,7 @@ alr_kernel(SysView s, int colour, float omega, int first_line, int nslots, int L
     // ---- phase C ----
     if (active && !(dbg & 4)) {
         for (int k = kfirst; k < n; k += KSTEP) {
-            const int i = DIR == 0 ? k : line, j = DIR == 0 ? line : k;
+            const int i = (DIR & 1) == 0 ? k : line, j = (DIR & 1) == 0 ? line : k;
             const int ip = j * nr + i;
             const int ch = (int)__umulhi((unsigned)k, magic);
             const int ad = ch * Lp + (k - ch * Lc);
@@ -347,9 +350,178 @@ int launch_alr(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int 
         attr_set[ctx->device & 15] = true;
     }
     dim3 grid((nslots + G - 1) / G, sys->batch);
-    PDEGPU_PROF(ctx, DIR == 0 ? "alr_kernel<dir0>" : "alr_kernel<dir1>", sweep_bytes<FAM>() * (double)nslots * n * sys->batch);
+    PDEGPU_PROF(ctx, DIR == 0 ? "alr_kernel<dir0>" : DIR == 1 ? "alr_kernel<dir1>" : "alr_kernel<dir1,transposed>", sweep_bytes<FAM>() * (double)nslots * n * sys->batch);
     alr_kernel<FAM, DIR, G, TPL><<<grid, TPL * G, smem, ctx->stream>>>(v, colour, omega, first, nslots, Lc, Lp, getenv("PDEGPU_DBG") ? atoi(getenv("PDEGPU_DBG")) : 0);
     PDEGPU_LAUNCH_CHECK(ctx, "alr_kernel");
+    return PDEGPU_OK;
+}
+
+// =============================================================================================
+// Pipelined variant: one persistent CTA per SM, warp-specialised.
+//   loader warps : phase A of line group t into stage t % S of a shared-memory ring, then phase C of
+//                  group t-(S-1) (which the solver warps have finished meanwhile);
+//   solver warps : phase B, one warp per line of the stage.
+// Stages hand over through mbarriers (full -> solved -> freed), so global loads, line solves and
+// stores of different line groups overlap and the HBM stream of an SM never pauses for a solve.
+// =============================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "MBAR_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra MBAR_DONE;\n"
+                 "bra MBAR_WAIT;\n"
+                 "MBAR_DONE:\n"
+                 "}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+template <int FAM, int DIR, int G, int NLW, int S>
+__global__ void __launch_bounds__((NLW + G) * 32, 1)
+alr_pipe_kernel(SysView s, int colour, float omega, int first_line, int nslots, int Lc, int Lp,
+                int groups_per_image, int total_groups)
+{
+    using F = Fam<FAM>;
+    using SL = Slots<F::NUNK>;
+    extern __shared__ float smem[];
+    constexpr int qa = (F::NUNK == 2 && DIR != 0) ? 1 : 0, qb = 1 - qa;
+    constexpr int NT = NLW * 32;                             // loader threads
+    const int nr = s.nrows, nc = s.ncols;
+    const int n = (DIR & 1) == 0 ? nr : nc;
+    const int NP = 32 * Lp;
+    const size_t stage_floats = (size_t)G * SL::N * NP;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + (size_t)S * stage_floats);
+    unsigned long long *full = bars, *solved = bars + S, *freed = bars + 2 * S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int k = 0; k < S; k++) { mbar_init(&full[k], NT); mbar_init(&solved[k], G * 32); mbar_init(&freed[k], NT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned magic = (unsigned)((0x100000000ull + (unsigned)Lc - 1) / (unsigned)Lc);
+    const int nit = (total_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // groups of this CTA
+
+    if (warp < NLW) {
+        // ------------------------------- loader / writer warps -------------------------------
+        constexpr int TPL = NT / G;
+        const int g = (DIR & 1) == 0 ? tid / TPL : tid % G;
+        const int kfirst = (DIR & 1) == 0 ? tid % TPL : tid / G;
+        constexpr int KSTEP = TPL;
+        constexpr int UNR = PDEGPU_ALR_UNR;
+        auto write_back = [&](int jt) {
+            const int gi = blockIdx.x + jt * gridDim.x;
+            const int b = gi / groups_per_image, slot0 = (gi - b * groups_per_image) * G;
+            const int line = first_line + colour + 2 * (slot0 + g);
+            const int st = jt % S;
+            mbar_wait(&solved[st], (jt / S) & 1);
+            if (slot0 + g < nslots) {
+                const float *Ls = smem + st * stage_floats + (size_t)g * SL::N * NP;
+                const int ibase = b * (int)s.bstride;
+                for (int k = kfirst; k < n; k += KSTEP) {
+                    const int i = (DIR & 1) == 0 ? k : line, j = (DIR & 1) == 0 ? line : k;
+                    const int ip = ibase + j * nr + i;
+                    const int ch = (int)__umulhi((unsigned)k, magic);
+                    const int ad = ch * Lp + (k - ch * Lc);
+                    s.x[qa][ip] = Ls[SL::D1 * NP + ad];
+                    if (F::NUNK == 2) {
+                        float *X2 = s.x[qb];
+                        X2[ip] = omega * Ls[SL::D2 * NP + ad] + (1.0f - omega) * X2[ip];
+                    }
+                }
+            }
+            mbar_arrive(&freed[st]);
+        };
+        for (int it = 0; it < nit; it++) {
+            const int gi = blockIdx.x + it * gridDim.x;
+            const int b = gi / groups_per_image, slot0 = (gi - b * groups_per_image) * G;
+            const int line = first_line + colour + 2 * (slot0 + g);
+            const int st = it % S;
+            if (it >= S) mbar_wait(&freed[st], ((it / S) - 1) & 1);
+            if (slot0 + g < nslots) {
+                float *Ls = smem + st * stage_floats + (size_t)g * SL::N * NP;
+                const int ibase = b * (int)s.bstride;
+                for (int k0 = kfirst; k0 < n; k0 += UNR * KSTEP) {
+                    PixelRaw<FAM, DIR> raw[UNR];
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        const int k = min(k0 + u * KSTEP, n - 1);
+                        const int i = (DIR & 1) == 0 ? k : line, j = (DIR & 1) == 0 ? line : k;
+                        raw[u].load(s, ibase + j * nr + i, i, j);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        const int k = min(k0 + u * KSTEP, n - 1);
+                        const int ch = (int)__umulhi((unsigned)k, magic);
+                        const int ad = ch * Lp + (k - ch * Lc);
+                        float a, c, bb[2], d[2], m;
+                        raw[u].rows(a, c, bb, d, m);
+                        Ls[SL::A * NP + ad] = a;
+                        Ls[SL::C * NP + ad] = c;
+                        Ls[SL::B1 * NP + ad] = bb[qa];
+                        Ls[SL::D1 * NP + ad] = d[qa];
+                        Ls[SL::XO * NP + ad] = raw[u].xo[qa];
+                        if (F::NUNK == 2) {
+                            Ls[SL::B2 * NP + ad] = bb[qb];
+                            Ls[SL::D2 * NP + ad] = d[qb];
+                            Ls[SL::M * NP + ad] = m;
+                        }
+                    }
+                }
+            }
+            mbar_arrive(&full[st]);
+            if (it >= S - 1) write_back(it - (S - 1));
+        }
+        for (int jt = max(0, nit - (S - 1)); jt < nit; jt++) write_back(jt);
+    } else {
+        // ------------------------------------ solver warps ------------------------------------
+        const int sw = warp - NLW;
+        for (int it = 0; it < nit; it++) {
+            const int gi = blockIdx.x + it * gridDim.x;
+            const int b = gi / groups_per_image, slot0 = (gi - b * groups_per_image) * G;
+            const int st = it % S;
+            mbar_wait(&full[st], (it / S) & 1);
+            if (slot0 + sw < nslots) {
+                float *Lw = smem + st * stage_floats + (size_t)sw * SL::N * NP;
+                warp_line_solve<false, true>(Lw + SL::A * NP, Lw + SL::C * NP, Lw + SL::B1 * NP, Lw + SL::D1 * NP, Lw + SL::GP * NP,
+                                             nullptr, nullptr, Lw + SL::XO * NP, n, Lc, Lp, omega, lane);
+                if (F::NUNK == 2) {
+                    __syncwarp();
+                    warp_line_solve<true, false>(Lw + SL::A * NP, Lw + SL::C * NP, Lw + SL::B2 * NP, Lw + SL::D2 * NP, Lw + SL::GP * NP,
+                                                 Lw + SL::M * NP, Lw + SL::D1 * NP, nullptr, n, Lc, Lp, omega, lane);
+                }
+            }
+            __syncwarp();
+            mbar_arrive(&solved[st]);
+        }
+    }
+}
+
+template <int FAM, int DIR, int G, int S>
+int launch_alr_pipe(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int colour, float omega,
+                    int first, int nslots, int n, int Lc, int Lp, size_t smem)
+{
+    constexpr int NLW = 16;
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(alr_pipe_kernel<FAM, DIR, G, NLW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_pipe_kernel)");
+        attr_set[ctx->device & 15] = true;
+    }
+    const int gpi = (nslots + G - 1) / G;
+    const int total = gpi * sys->batch;
+    const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+    PDEGPU_PROF(ctx, DIR == 0 ? "alr_pipe_kernel<dir0>" : DIR == 1 ? "alr_pipe_kernel<dir1>" : "alr_pipe_kernel<dir1,transposed>", sweep_bytes<FAM>() * (double)nslots * n * sys->batch);
+    alr_pipe_kernel<FAM, DIR, G, NLW, S><<<grid, (NLW + G) * 32, smem, ctx->stream>>>(v, colour, omega, first, nslots, Lc, Lp, gpi, total);
+    PDEGPU_LAUNCH_CHECK(ctx, "alr_pipe_kernel");
     return PDEGPU_OK;
 }
 
@@ -358,18 +530,30 @@ int alr_pass(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int co
 {
     using F = Fam<FAM>;
     constexpr bool INTERIOR_ONLY = F::PDE && F::EIGHT;
-    const int nlines = DIR == 0 ? sys->ncols : sys->nrows;
-    const int n = DIR == 0 ? sys->nrows : sys->ncols;
+    const int nlines = (DIR & 1) == 0 ? sys->ncols : sys->nrows;
+    const int n = (DIR & 1) == 0 ? sys->nrows : sys->ncols;
     const int first = INTERIOR_ONLY ? 1 : 0, last = INTERIOR_ONLY ? nlines - 2 : nlines - 1;
     if (first + colour > last) return PDEGPU_OK;
     const int nslots = (last - (first + colour)) / 2 + 1;
     const int Lc = (n + 31) / 32, Lp = Lc | 1;
     const size_t line_bytes = (size_t)Slots<F::NUNK>::N * 32 * Lp * sizeof(float);
+    // pipelined persistent kernel when a ring of >= 2 stages x 4 lines fits and there is enough work to stream
+    {
+        static const int use_pipe = getenv("PDEGPU_ALR_PIPE") ? atoi(getenv("PDEGPU_ALR_PIPE")) : 1;
+        const size_t room = 227 * 1024 - 256;
+        const long long groups = (long long)((nslots + 3) / 4) * sys->batch;
+        const bool idx_ok = (long long)sys->batch * sys->batch_stride < (1ll << 31);
+        if (use_pipe && idx_ok && groups >= 2 * ctx->sm_count && 2 * 4 * line_bytes <= room) {
+            if (3 * 4 * line_bytes <= room)
+                return launch_alr_pipe<FAM, DIR, 4, 3>(ctx, v, sys, colour, omega, first, nslots, n, Lc, Lp, 3 * 4 * line_bytes + 256);
+            return launch_alr_pipe<FAM, DIR, 4, 2>(ctx, v, sys, colour, omega, first, nslots, n, Lc, Lp, 2 * 4 * line_bytes + 256);
+        }
+    }
     // G lines per CTA: as many as keep >= 2 CTAs per SM resident; lines along j (DIR 1) are strided in
     // memory, so they want >= 4 neighbouring lines per CTA to use the sectors they fetch.
     int G = 8;
     while (G > 1 && G * line_bytes > (size_t)kMaxSmem / 2) G >>= 1;
-    if (DIR == 1 && G < 4) { G = 4; while (G > 1 && G * line_bytes > (size_t)kMaxSmem) G >>= 1; }
+    if ((DIR & 1) == 1 && G < 4) { G = 4; while (G > 1 && G * line_bytes > (size_t)kMaxSmem) G >>= 1; }
     if (G * line_bytes > (size_t)kMaxSmem) return PDEGPU_ERR_UNSUPPORTED;   // line too long for shared memory
     const size_t smem = G * line_bytes;
     switch (G) {
@@ -380,22 +564,102 @@ int alr_pass(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int co
     }
 }
 
+// Batched transpose of dense column-major fields: dst[b][i*ncols + j] = src[b*sstride + j*nrows + i].
+__global__ void __launch_bounds__(256)
+transpose_kernel(float *__restrict__ dst, const float *__restrict__ src, int nrows, int ncols, long long sstride, long long dstride)
+{
+    __shared__ float tile[32][33];
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    src += (long long)blockIdx.z * sstride;
+    dst += (long long)blockIdx.z * dstride;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + tx, j = j0 + r;
+        if (i < nrows && j < ncols) tile[r][tx] = src[(long long)j * nrows + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + tx, i = i0 + r;
+        if (i < nrows && j < ncols) dst[(long long)i * ncols + j] = tile[tx][r];
+    }
+}
+
+int transpose_fields(pdegpu_ctx *ctx, float *dst, const float *src, int nrows, int ncols, int batch, long long sstride, long long dstride)
+{
+    dim3 grid((nrows + 31) / 32, (ncols + 31) / 32, batch);
+    PDEGPU_PROF(ctx, "transpose_kernel", 0);
+    transpose_kernel<<<grid, 256, 0, ctx->stream>>>(dst, src, nrows, ncols, sstride, dstride);
+    PDEGPU_LAUNCH_CHECK(ctx, "transpose_kernel");
+    return PDEGPU_OK;
+}
+
+// One ALR iteration = lines along i (both colours), then lines along j (both colours). Lines along j are
+// strided in memory: a CTA that owns a few of them touches one 32-B sector per element and uses half of
+// it (zebra), and the sweep becomes L1-wavefront-bound (measured: 2x the DRAM bytes and 2x the time of the
+// contiguous direction). So the row pass runs on a TRANSPOSED copy of the problem, where its lines are
+// contiguous too: coefficients are transposed once per call, the unknowns twice per iteration (16 B/px
+// each way, against ~150 B/px for a sweep).
 template <int FAM>
 int alr_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
+    using F = Fam<FAM>;
     SysView v = make_view(sys);
-    if (Fam<FAM>::PDE && Fam<FAM>::EIGHT) iter = 1;            // pdeSolvers.c:362
+    if (F::PDE && F::EIGHT) iter = 1;            // pdeSolvers.c:362
     // refuse up front (before touching the unknowns) if either direction does not fit
     if ((long long)sys->nrows * sys->ncols >= (1ll << 31) || sys->nrows >= 65536 || sys->ncols >= 65536) return PDEGPU_ERR_UNSUPPORTED;
     {
-        const size_t per = (size_t)Slots<Fam<FAM>::NUNK>::N * 32 * sizeof(float);
+        const size_t per = (size_t)Slots<F::NUNK>::N * 32 * sizeof(float);
         const int L0 = ((sys->nrows + 31) / 32) | 1, L1 = ((sys->ncols + 31) / 32) | 1;
         if (per * L0 > (size_t)kMaxSmem || per * L1 > (size_t)kMaxSmem) return PDEGPU_ERR_UNSUPPORTED;
     }
+    constexpr int NN = F::EIGHT ? 8 : 4;
+    const long long npix = (long long)sys->nrows * sys->ncols;
+    static const int use_xpose = getenv("PDEGPU_ALR_XPOSE") ? atoi(getenv("PDEGPU_ALR_XPOSE")) : 1;
+    const int nfields = NN + 3 * F::NUNK + (F::NUNK == 2 ? 1 : 0) + (F::LATE ? F::NUNK : 0);
+    bool xpose = use_xpose && sys->nrows >= 8 && sys->ncols >= 8;
+    pdegpu_system tsys = *sys;
+    float *xT[2] = {nullptr, nullptr};
     int rc;
+    if (xpose) {
+        if (pdegpu_scratch_reserve(ctx, (size_t)nfields * npix * sys->batch * sizeof(float)) != PDEGPU_OK) xpose = false;
+    }
+    if (xpose) {
+        float *p = (float *)ctx->scratch;
+        auto take = [&]() { float *r = p; p += npix * sys->batch; return r; };
+        auto tr = [&](const float *src) -> float * {
+            float *d = take();
+            rc = transpose_fields(ctx, d, src, sys->nrows, sys->ncols, sys->batch, sys->batch_stride, npix);
+            return d;
+        };
+        // neighbour roles swap under transposition: N<->W, S<->E, NE<->SW
+        static const int perm[8] = {W_N, W_W, W_S, W_E, W_NW, W_SW, W_SE, W_NE};
+        rc = PDEGPU_OK;
+        tsys.nrows = sys->ncols; tsys.ncols = sys->nrows; tsys.batch_stride = npix;
+        for (int n = 0; n < NN && !rc; n++) tsys.w[n] = tr(sys->w[perm[n]]);
+        for (int q = 0; q < F::NUNK && !rc; q++) {
+            tsys.c[q] = tr(sys->c[q]);
+            if (!rc) tsys.d[q] = tr(sys->d[q]);
+            if (F::LATE && !rc) tsys.x0[q] = tr(sys->x0[q]);
+            xT[q] = take();
+            tsys.x[q] = xT[q];
+        }
+        if (F::NUNK == 2 && !rc) tsys.m = tr(sys->m);
+        if (rc) return rc;
+    }
+    SysView vt = make_view(&tsys);
     for (int it = 0; it < iter; it++) {
         for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 0>(ctx, v, sys, colour, omega))) return rc;
-        for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 1>(ctx, v, sys, colour, omega))) return rc;
+        if (xpose) {
+            for (int q = 0; q < F::NUNK; q++)
+                if ((rc = transpose_fields(ctx, xT[q], sys->x[q], sys->nrows, sys->ncols, sys->batch, sys->batch_stride, npix))) return rc;
+            for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 2>(ctx, vt, &tsys, colour, omega))) return rc;
+            for (int q = 0; q < F::NUNK; q++)
+                if ((rc = transpose_fields(ctx, sys->x[q], xT[q], sys->ncols, sys->nrows, sys->batch, npix, sys->batch_stride))) return rc;
+        } else {
+            for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 1>(ctx, v, sys, colour, omega))) return rc;
+        }
     }
     return PDEGPU_OK;
 }

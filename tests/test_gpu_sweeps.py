@@ -192,3 +192,46 @@ def test_kernel_generations_agree(built, fam, solver, shape):
             assert_bitwise(a, b, f"{fam} point")
         else:
             assert rel_err(a, b) < 2e-5
+
+
+@pytest.mark.parametrize("shape,batch", [((96, 128), 40), ((131, 67), 48), ((480, 640), 8)])
+@pytest.mark.parametrize("fam", ["llin4", "pde4"])
+def test_pipelined_line_kernel_on_batches(built, fam, shape, batch):
+    """Enough line groups to take the persistent, warp-specialised ALR kernel (>= 2 groups per SM):
+    every problem of the batch must match the generation-0 kernels."""
+    import torch
+    from pdegpu import lib
+    nr, nc = shape
+    n = nr * nc
+    ctx = lib.Context(0)
+    dev = torch.device("cuda:0")
+    if fam == "llin4":
+        systems = [synth.flow_system(500 + b, nr, nc, late=True) for b in range(4)]
+        keys = ("U", "V", "dU", "dV", "M", "Cu", "Cv", "Du", "Dv", "wW", "wN", "wE", "wS")
+    else:
+        systems = [synth.pde_system(600 + b, nr, nc) for b in range(4)]
+        keys = ("X", "TRACE", "B", "wW", "wN", "wE", "wS")
+    t = {k: torch.from_numpy(np.stack([systems[b % 4][k].reshape(-1, order="F") for b in range(batch)])).to(dev) for k in keys}
+
+    def mk(x):
+        if fam == "llin4":
+            return lib.make_system(lib.FLOW_LLIN4, nr, nc, batch=batch, batch_stride=n, x=(x[0].data_ptr(), x[1].data_ptr()),
+                                   x0=(t["U"].data_ptr(), t["V"].data_ptr()), m=t["M"].data_ptr(),
+                                   c=(t["Cu"].data_ptr(), t["Cv"].data_ptr()), d=(t["Du"].data_ptr(), t["Dv"].data_ptr()),
+                                   w=[t[k].data_ptr() for k in ("wW", "wN", "wE", "wS")])
+        return lib.make_system(lib.PDE4, nr, nc, batch=batch, batch_stride=n, x=(x[0].data_ptr(),),
+                               c=(t["B"].data_ptr(),), d=(t["TRACE"].data_ptr(),),
+                               w=[t[k].data_ptr() for k in ("wW", "wN", "wE", "wS")])
+
+    res = []
+    for path in (0, 1):
+        ctx.set_kernel_path(path)
+        x = [t["dU"].clone(), t["dV"].clone()] if fam == "llin4" else [t["X"].clone()]
+        torch.cuda.synchronize()
+        ctx.relax(mk(x), 3, 1.9, 2)
+        ctx.sync()
+        res.append([a.cpu().numpy() for a in x])
+    ctx.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.isfinite(b).all()
+        assert rel_err(a, b) < 2e-5
