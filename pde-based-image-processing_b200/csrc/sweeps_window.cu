@@ -1,0 +1,571 @@
+// sweeps_window.cu -- kernel generation 2, solver 2: zebra line relaxation as a SLIDING WINDOW.
+//
+// One launch = one complete direction pass (BOTH colours, both unknowns) over a batch of problems,
+// reading every field exactly once and writing every unknown exactly once:
+//
+//   * The lines of the pass are contiguous in memory (the row pass runs on a transposed copy of the
+//     problem, see alr_window_run). A persistent CTA (one per SM) owns a contiguous range of 8-line
+//     blocks of the batch and walks through it line by line.
+//   * Zebra order "all even lines, then all odd lines" only constrains neighbours: an odd line needs the
+//     NEW values of its two even neighbours, an even line the OLD values of its two odd neighbours. So the
+//     CTA relaxes  e0 e2 .. e(2D-2) | e(2D) o1 e(2D+2) o3 ...  -- mathematically the same sweep -- and each
+//     line's coefficients are touched once. The pass is out of place (reads X_in, writes X_out), so old
+//     values are always available from global memory; new even values are handed to the odd lines through
+//     a ring of solved lines in shared memory. The last odd line of a CTA's range needs the first even line
+//     of the next range: that one line is solved redundantly (same inputs, same code => same bits).
+//   * One WARP per line does everything for it: coalesced global loads (element e = 32t + lane), the
+//     reference's tridiagonal row per pixel (line_rows.cuh), a transposition through a private
+//     shared-memory scratch to "lane = chunk of M consecutive unknowns", then a partitioned Thomas solve
+//     held entirely in registers (local elimination with a left spike, a 32-unknown interface system
+//     solved by parallel cyclic reduction on shuffles, local back substitution), SOR, and the result into
+//     the ring. 5-8 warps of a CTA work on different lines at any time; warps synchronise only through
+//     per-line "solved" and per-block "written" sequence numbers in shared memory.
+//   * X_out is written in the TRANSPOSED layout, 8 lines at a time (one full 32-B sector per element), by
+//     the warp that completes a block. The next direction pass wants exactly that layout, so alternating
+//     directions costs no transposition of the unknowns at all.
+//
+// HBM traffic per pass = algorithmic: (#fields read + #unknowns written) * 4 B per pixel (+ 1 line per
+// CTA range). Same fixed point and same ordering semantics as generation 0/1 (even lines first).
+#include "line_rows.cuh"
+#include <stdlib.h>
+
+namespace {
+
+struct WinParams {
+    SysView s;             // problem with contiguous lines (lines = columns of s); s.x = X_in
+    float *xout[2];        // X_out, transposed layout: element i of line j of problem b at b*ostride + i*nlines + j
+    long long ostride;
+    int n, nlines;         // line length (= s.nrows), lines per problem (= s.ncols)
+    int NB, TB;            // 8-line blocks per problem, in total
+    int R, D;              // ring size in lines (multiple of 8), how many pairs the even lines run ahead
+    int vec_ok;            // float4 stores of X_out are aligned
+    float omega;
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+// Whole warp waits until *p >= want. A wait that never ends is a scheduling bug: trap instead of hanging the GPU.
+__device__ __forceinline__ void warp_wait_ge(const unsigned *p, unsigned want, int lane)
+{
+    if (lane == 0) {
+        unsigned spins = 0;
+        while (ld_acquire(p) < want) {
+            __nanosleep(100);
+            if (++spins > (1u << 23)) __trap();
+        }
+    }
+    __syncwarp();
+}
+
+// Partitioned Thomas solve of one line spread over the warp: lane L holds rows L*M .. L*M+M-1 of
+//   a_k x_{k-1} + b_k x_k + c_k x_{k+1} = d_k
+// (rows past the end of the line are identity rows). On return d[] holds x. a, b are clobbered.
+template <int M>
+__device__ __forceinline__ void chunk_solve(float (&a)[M], const float (&c)[M], float (&b)[M], float (&d)[M], int lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    // local forward elimination; spike a[] multiplies x_left = last unknown of the previous lane.
+    // afterwards row k reads  x_k + b[k]*x_{k+1} + a[k]*x_left = d[k]
+    {
+        const float inv = fast_rcp(b[0]);
+        b[0] = c[0] * inv; d[0] *= inv; a[0] *= inv;
+    }
+#pragma unroll
+    for (int k = 1; k < M; k++) {
+        const float ak = a[k];
+        const float inv = fast_rcp(b[k] - ak * b[k - 1]);
+        b[k] = c[k] * inv;
+        d[k] = (d[k] - ak * d[k - 1]) * inv;
+        a[k] = (-ak * a[k - 1]) * inv;
+    }
+    // first unknown of the chunk in terms of the last one and x_left:  x_first = Af - Bf*x_last - Gf*x_left
+    float Af, Bf, Gf;
+    if (M == 1) { Af = 0.f; Bf = -1.0f; Gf = 0.f; }
+    else {
+        Af = d[M - 2]; Bf = b[M - 2]; Gf = a[M - 2];
+#pragma unroll
+        for (int r = M - 3; r >= 0; r--) {
+            Af = d[r] - b[r] * Af;
+            Bf = -b[r] * Bf;
+            Gf = a[r] - b[r] * Gf;
+        }
+    }
+    // interface system in the lanes' last unknowns l:  al*l[-1] + be*l + ga*l[+1] = de
+    float An = __shfl_down_sync(FULL, Af, 1), Bn = __shfl_down_sync(FULL, Bf, 1), Gn = __shfl_down_sync(FULL, Gf, 1);
+    if (lane == 31) { An = 0.f; Bn = 0.f; Gn = 0.f; }
+    const float cp = b[M - 1];
+    float al = a[M - 1], be = 1.0f - cp * Gn, ga = -cp * Bn, de = d[M - 1] - cp * An;
+#pragma unroll
+    for (int st = 1; st < 32; st <<= 1) {
+        float alm = __shfl_up_sync(FULL, al, st), bem = __shfl_up_sync(FULL, be, st);
+        float gam = __shfl_up_sync(FULL, ga, st), dem = __shfl_up_sync(FULL, de, st);
+        float alp = __shfl_down_sync(FULL, al, st), bep = __shfl_down_sync(FULL, be, st);
+        float gap = __shfl_down_sync(FULL, ga, st), dep = __shfl_down_sync(FULL, de, st);
+        if (lane < st)      { alm = 0.f; bem = 1.0f; gam = 0.f; dem = 0.f; }
+        if (lane + st > 31) { alp = 0.f; bep = 1.0f; gap = 0.f; dep = 0.f; }
+        const float k1 = al * fast_rcp(bem), k2 = ga * fast_rcp(bep);
+        be = be - gam * k1 - alp * k2;
+        de = de - dem * k1 - dep * k2;
+        al = -alm * k1;
+        ga = -gap * k2;
+    }
+    const float l = de * fast_rcp(be);
+    float L = __shfl_up_sync(FULL, l, 1);
+    if (lane == 0) L = 0.f;
+    // local back substitution
+    float x = l;
+    d[M - 1] = x;
+#pragma unroll
+    for (int r = M - 2; r >= 0; r--) {
+        x = d[r] - b[r] * x - a[r] * L;
+        d[r] = x;
+    }
+}
+
+template <int NUNK> struct RowF;
+template <> struct RowF<2> { enum { A = 0, C = 1, B1 = 2, D1 = 3, B2 = 4, D2 = 5, MM = 6, N = 7 }; };
+template <> struct RowF<1> { enum { A = 0, C = 1, B1 = 2, D1 = 3, B2 = 2, D2 = 3, MM = 0, N = 4 }; };
+
+constexpr int kWinMaxWarps = 8;
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+#define V4(v, kk) ((kk) == 0 ? (v).x : (kk) == 1 ? (v).y : (kk) == 2 ? (v).z : (v).w)
+
+// one line of a CTA's schedule
+struct WinTask {
+    int l, img, jb, j, ibase, dW, dE;
+    bool odd, eW, eE, owned;
+};
+
+// Raw operands of 4 consecutive pixels of a line (one float4 per field), loaded with no use of the values,
+// so that a lane can have the loads of two batches in flight.
+template <int FAM>
+struct RawBatch {
+    using F = Fam<FAM>;
+    static constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, NL = F::LATE ? F::NUNK : 1;
+    float4 w4[NN], C4[NUNK], D4[NUNK], XO4[NUNK], XW4[NUNK], XE4[NUNK], M4;
+    float4 X0C4[NL], X0W4[NL], X0E4[NL];
+    float x0l[NUNK], x0r[NUNK];                                    // in-line neighbours beyond the vector
+    float xWl[NUNK], xWr[NUNK], xEl[NUNK], xEr[NUNK];              // 8-neighbour: diagonal neighbours beyond the vector
+    float x0Wl[NUNK], x0Wr[NUNK], x0El[NUNK], x0Er[NUNK];
+
+    // ec = first element (clamped into the line), T = the line
+    __device__ __forceinline__ void issue(const SysView &s, const WinTask &T, int ec, int n)
+    {
+        const int ip = T.ibase + ec;
+        const int ipl = T.ibase + max(ec - 1, 0), ipr = T.ibase + min(ec + 4, n - 1);
+        const int dW = T.dW, dE = T.dE;
+#pragma unroll
+        for (int nn = 0; nn < NN; nn++) w4[nn] = ld4(s.w[nn] + ip);
+#pragma unroll
+        for (int qq = 0; qq < NUNK; qq++) {
+            C4[qq] = ld4(s.c[qq] + ip); D4[qq] = ld4(s.d[qq] + ip); XO4[qq] = ld4(s.x[qq] + ip);
+            if (F::LATE) {
+                X0C4[qq] = ld4(s.x0[qq] + ip); X0W4[qq] = ld4(s.x0[qq] + ip + dW); X0E4[qq] = ld4(s.x0[qq] + ip + dE);
+                x0l[qq] = s.x0[qq][ipl]; x0r[qq] = s.x0[qq][ipr];
+                if (F::EIGHT) {
+                    x0Wl[qq] = s.x0[qq][ipl + dW]; x0Wr[qq] = s.x0[qq][ipr + dW];
+                    x0El[qq] = s.x0[qq][ipl + dE]; x0Er[qq] = s.x0[qq][ipr + dE];
+                }
+            }
+            if (!T.odd) {
+                XW4[qq] = ld4(s.x[qq] + ip + dW); XE4[qq] = ld4(s.x[qq] + ip + dE);
+                if (F::EIGHT) {
+                    xWl[qq] = s.x[qq][ipl + dW]; xWr[qq] = s.x[qq][ipr + dW];
+                    xEl[qq] = s.x[qq][ipl + dE]; xEr[qq] = s.x[qq][ipr + dE];
+                }
+            }
+        }
+        if (NUNK == 2) M4 = ld4(s.m + ip);
+    }
+
+    // odd lines: the unknowns at the (even) neighbour lines come from the ring of solved lines
+    __device__ __forceinline__ void neighbours_from_ring(const float *rsW, const float *rsE, int P, int ec, int n)
+    {
+#pragma unroll
+        for (int qq = 0; qq < NUNK; qq++) {
+            XW4[qq] = ld4(rsW + qq * P + ec); XE4[qq] = ld4(rsE + qq * P + ec);
+            if (F::EIGHT) {
+                xWl[qq] = rsW[qq * P + max(ec - 1, 0)]; xWr[qq] = rsW[qq * P + min(ec + 4, n - 1)];
+                xEl[qq] = rsE[qq * P + max(ec - 1, 0)]; xEr[qq] = rsE[qq * P + min(ec + 4, n - 1)];
+            }
+        }
+    }
+
+    // operands of pixel k (0..3) of the vector, in the form the row formulas take
+    template <int DIR>
+    __device__ __forceinline__ void pixel(int k, int i, int n, bool eW, bool eE, PixelRaw<FAM, DIR> &r) const
+    {
+        const bool eN = i > 0, eS = i < n - 1;
+        r.exmask = (eW ? 1u << W_W : 0u) | (eN ? 1u << W_N : 0u) | (eE ? 1u << W_E : 0u) | (eS ? 1u << W_S : 0u)
+                 | (eN && eW ? 1u << W_NW : 0u) | (eN && eE ? 1u << W_NE : 0u) | (eS && eE ? 1u << W_SE : 0u) | (eS && eW ? 1u << W_SW : 0u);
+#pragma unroll
+        for (int nn = 0; nn < NN; nn++) r.w[nn] = V4(w4[nn], k);
+#pragma unroll
+        for (int qq = 0; qq < NUNK; qq++) {
+            r.C[qq] = V4(C4[qq], k); r.D[qq] = V4(D4[qq], k); r.xo[qq] = V4(XO4[qq], k);
+            r.xn[qq][W_W] = V4(XW4[qq], k); r.xn[qq][W_E] = V4(XE4[qq], k);
+            if (F::EIGHT) {
+                r.xn[qq][W_NW % NN] = k > 0 ? V4(XW4[qq], k - 1) : xWl[qq];
+                r.xn[qq][W_SW % NN] = k < 3 ? V4(XW4[qq], k + 1) : xWr[qq];
+                r.xn[qq][W_NE % NN] = k > 0 ? V4(XE4[qq], k - 1) : xEl[qq];
+                r.xn[qq][W_SE % NN] = k < 3 ? V4(XE4[qq], k + 1) : xEr[qq];
+            }
+            if (F::LATE) {
+                r.x0c[qq] = V4(X0C4[qq], k);
+                r.x0n[qq][W_W] = V4(X0W4[qq], k); r.x0n[qq][W_E] = V4(X0E4[qq], k);
+                r.x0n[qq][W_N] = k > 0 ? V4(X0C4[qq], k - 1) : x0l[qq];
+                r.x0n[qq][W_S] = k < 3 ? V4(X0C4[qq], k + 1) : x0r[qq];
+                if (F::EIGHT) {
+                    r.x0n[qq][W_NW % NN] = k > 0 ? V4(X0W4[qq], k - 1) : x0Wl[qq];
+                    r.x0n[qq][W_SW % NN] = k < 3 ? V4(X0W4[qq], k + 1) : x0Wr[qq];
+                    r.x0n[qq][W_NE % NN] = k > 0 ? V4(X0E4[qq], k - 1) : x0El[qq];
+                    r.x0n[qq][W_SE % NN] = k < 3 ? V4(X0E4[qq], k + 1) : x0Er[qq];
+                }
+            }
+        }
+        r.M = NUNK == 2 ? V4(M4, k) : 0.f;
+    }
+};
+
+// M is odd: lane L's chunk [L*M, L*M+M) is read with stride M (conflict-free), and a line sits in shared
+// memory in natural order, so 4 consecutive elements are one aligned float4.
+template <int FAM, int DIR, int M>
+__global__ void __launch_bounds__(kWinMaxWarps * 32, 1)
+alr_window_kernel(const WinParams p)
+{
+    using F = Fam<FAM>;
+    using RF = RowF<F::NUNK>;
+    static_assert(M & 1, "chunk length must be odd");
+    constexpr int NUNK = F::NUNK;
+    constexpr int qa = (NUNK == 2 && DIR != 0) ? 1 : 0, qb = 1 - qa;
+    constexpr int LS = 32 * M;                   // floats per line (padded with identity rows)
+    constexpr int P = LS;                        // ring pitch per unknown
+    constexpr int SP = NUNK * P + 4;             // ring pitch per line: = 4 mod 8, so the two half-warps of a block write hit disjoint banks
+    constexpr int NT = ((LS + 127) / 128 + 1) & ~1;   // batches of 128 elements (4 per lane), made even for the double buffer
+    extern __shared__ float smem[];
+    const int R = p.R, D = p.D, NBR = R >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float *ring = smem;
+    float *scratch = ring + (size_t)R * SP + (size_t)warp * RF::N * LS;
+    unsigned *flags = reinterpret_cast<unsigned *>(ring + (size_t)R * SP + (size_t)nwarps * RF::N * LS);
+    unsigned *solved_seq = flags, *written_seq = flags + R, *block_cnt = flags + R + NBR;
+    for (int t = threadIdx.x; t < R + 2 * NBR; t += blockDim.x) flags[t] = 0;
+    __syncthreads();
+
+    const int n = p.n, nlines = p.nlines;
+    const SysView &s = p.s;
+    // this CTA's range of blocks
+    const int B0 = (int)((long long)blockIdx.x * p.TB / gridDim.x), B1 = (int)((long long)(blockIdx.x + 1) * p.TB / gridDim.x);
+    const int nblk = B1 - B0;
+    const bool redundant = B1 < p.TB && (B1 % p.NB) != 0;    // first even line of the next range, solved here too
+    const int Ltot = 8 * nblk + (redundant ? 1 : 0);
+    const int Q = D + 2 * ((Ltot + 1) >> 1);
+    const float omega = p.omega, om1 = 1.0f - p.omega;
+
+    // schedule entry q -> line (evens run D pairs ahead of the odds); false if q names no line
+    auto decode = [&](int q, WinTask &T) -> bool {
+        if (q < D) { T.l = 2 * q; T.odd = false; }
+        else {
+            const int r = q - D;
+            if (r & 1) { T.l = r; T.odd = true; } else { T.l = 2 * D + r; T.odd = false; }
+        }
+        if (T.l >= Ltot) return false;
+        const int lb = T.l >> 3, gb = B0 + lb;
+        T.img = gb / p.NB; T.jb = gb - T.img * p.NB;
+        T.j = 8 * T.jb + (T.l & 7);
+        if (T.j >= nlines) return false;
+        T.owned = lb < nblk;
+        T.ibase = T.img * (int)s.bstride + T.j * n;
+        T.eW = T.j > 0; T.eE = T.j + 1 < nlines;
+        T.dW = T.eW ? -n : 0; T.dE = T.eE ? n : 0;
+        return true;
+    };
+    auto first_element = [&](int t, int &e0, int &ec) { e0 = 128 * t + 4 * lane; ec = e0 < n ? e0 : n - 4; };
+
+    RawBatch<FAM> raw[2];
+    WinTask cur, nxt;
+    int q = warp;
+    while (q < Q && !decode(q, cur)) q += nwarps;
+    if (q < Q) { int e0, ec; first_element(0, e0, ec); raw[0].issue(s, cur, ec, n); }
+
+    while (q < Q) {
+        int q2 = q + nwarps;
+        while (q2 < Q && !decode(q2, nxt)) q2 += nwarps;
+        const int l = cur.l, lb = l >> 3;
+        // the ring slot of this line must be free: its previous occupant (line l-R) has been written out and
+        // consumed by its odd neighbours, i.e. its block and the block before are written
+        if (l >= R) {
+            const int lbp = (l - R) >> 3;
+            warp_wait_ge(&written_seq[lbp % NBR], (unsigned)lbp + 1, lane);
+            if (lbp > 0) warp_wait_ge(&written_seq[(lbp - 1) % NBR], (unsigned)lbp, lane);
+        }
+        float *rs = ring + (size_t)(l % R) * SP;
+        const float *rsW = ring + (size_t)((l + R - 1) % R) * SP, *rsE = ring + (size_t)((l + 1) % R) * SP;
+
+        // ---- load + row assembly: lane holds elements 128*t + 4*lane .. +3; the loads of the next batch (or of
+        //      the first batch of this warp's next line) are issued before this batch is touched ----
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            {
+                int e0n, ecn;
+                if (t + 1 < NT) { first_element(t + 1, e0n, ecn); if (e0n < LS) raw[(t + 1) & 1].issue(s, cur, ecn, n); }
+                else if (q2 < Q) { first_element(0, e0n, ecn); raw[0].issue(s, nxt, ecn, n); }
+            }
+            int e0, ec;
+            first_element(t, e0, ec);
+            if (t == 0 && cur.odd) {
+                // new values of the even neighbours
+                warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
+                if (cur.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
+            }
+            if (e0 < LS) {
+                RawBatch<FAM> &rb = raw[t & 1];
+                if (cur.odd) rb.neighbours_from_ring(rsW, rsE, P, ec, n);
+                const bool valid = e0 < n;
+                float ra[4], rc[4], rb1[4], rd1[4], rb2[4], rd2[4], rm[4], xo0[4], xo1[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    PixelRaw<FAM, DIR> r;
+                    rb.template pixel<DIR>(k, ec + k, n, cur.eW, cur.eE, r);
+                    float a, c, b[2], d[2], m;
+                    r.rows(a, c, b, d, m);
+                    ra[k] = valid ? a : 0.f; rc[k] = valid ? c : 0.f;
+                    rb1[k] = valid ? b[qa] : 1.0f; rd1[k] = valid ? d[qa] : 0.f;
+                    rb2[k] = valid ? b[qb] : 1.0f; rd2[k] = valid ? d[qb] : 0.f;
+                    rm[k] = valid ? m : 0.f;
+                    xo0[k] = valid ? r.xo[0] : 0.f; xo1[k] = (valid && NUNK == 2) ? r.xo[NUNK - 1] : 0.f;
+                }
+                st4(scratch + RF::A * LS + e0, ra);
+                st4(scratch + RF::C * LS + e0, rc);
+                st4(scratch + RF::B1 * LS + e0, rb1);
+                st4(scratch + RF::D1 * LS + e0, rd1);
+                st4(rs + e0, xo0);
+                if (NUNK == 2) {
+                    st4(scratch + RF::B2 * LS + e0, rb2);
+                    st4(scratch + RF::D2 * LS + e0, rd2);
+                    st4(scratch + RF::MM * LS + e0, rm);
+                    st4(rs + P + e0, xo1);
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- solve, lane = chunk ----
+        {
+            const int o = lane * M;
+            float a[M], c[M], b[M], d[M];
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                a[k] = scratch[RF::A * LS + o + k]; c[k] = scratch[RF::C * LS + o + k];
+                b[k] = scratch[RF::B1 * LS + o + k]; d[k] = scratch[RF::D1 * LS + o + k];
+            }
+            chunk_solve<M>(a, c, b, d, lane);
+#pragma unroll
+            for (int k = 0; k < M; k++) {
+                d[k] = omega * d[k] + om1 * rs[qa * P + o + k];
+                rs[qa * P + o + k] = d[k];
+            }
+            if (NUNK == 2) {
+#pragma unroll
+                for (int k = 0; k < M; k++) {
+                    a[k] = scratch[RF::A * LS + o + k];
+                    b[k] = scratch[RF::B2 * LS + o + k];
+                    d[k] = scratch[RF::D2 * LS + o + k] - scratch[RF::MM * LS + o + k] * d[k];
+                }
+                chunk_solve<M>(a, c, b, d, lane);
+#pragma unroll
+                for (int k = 0; k < M; k++) rs[qb * P + o + k] = omega * d[k] + om1 * rs[qb * P + o + k];
+            }
+        }
+        __syncwarp();
+        unsigned done = 0;
+        if (lane == 0) {
+            st_release(&solved_seq[l % R], (unsigned)l + 1);
+            __threadfence_block();
+            if (cur.owned) done = atomicAdd(&block_cnt[lb % NBR], 1u) + 1;
+        }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        const int j0 = 8 * cur.jb, cnt = min(8, nlines - j0);
+        if (cur.owned && (int)done == cnt) {
+            // ---- this warp completed block lb: write its lines to X_out (transposed layout) ----
+            __threadfence_block();
+            const float *rblk = ring + (size_t)((8 * lb) % R) * SP;
+#pragma unroll
+            for (int qq = 0; qq < NUNK; qq++) {
+                float *o = p.xout[qq] + (long long)cur.img * p.ostride + j0;
+                const float *rq = rblk + qq * P;
+                if (cnt == 8 && p.vec_ok) {
+                    // half-warp h writes lines 4h..4h+3 of 16 consecutive elements: full 32-B sectors
+                    const int h = lane >> 4;
+                    const float *rh = rq + (size_t)(4 * h) * SP;
+#pragma unroll 2
+                    for (int i = lane & 15; i < n; i += 16) {
+                        float4 v;
+                        v.x = rh[i]; v.y = rh[SP + i]; v.z = rh[2 * SP + i]; v.w = rh[3 * SP + i];
+                        *reinterpret_cast<float4 *>(o + (long long)i * nlines + 4 * h) = v;
+                    }
+                } else {
+                    const int k = lane & 7;
+                    for (int i = lane >> 3; i < n; i += 4)
+                        if (k < cnt) o[(long long)i * nlines + k] = rq[(size_t)k * SP + i];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                block_cnt[lb % NBR] = 0;
+                st_release(&written_seq[lb % NBR], (unsigned)lb + 1);
+            }
+        }
+        q = q2;
+        cur = nxt;
+    }
+}
+#undef V4
+
+struct WinGeom { int M, LS, SP, R, D, NW; size_t smem; };
+
+// Ring + per-warp scratch must fit in one SM's shared memory. With NW lines in flight, the evens must run
+// D pairs ahead of the odds with 2D-1 >= NW (an odd line then finds its even neighbours solved), and the
+// ring must span the evens' lead, the lines in flight and a block waiting to be written: R >= 2D + NW + 9
+// (which also gives R > 7 + 2D, the condition for the schedule to be free of deadlock, tools/window_schedule_sim.py).
+static bool win_geometry(int n, int nunk, WinGeom &g)
+{
+    static const int Ms[] = {5, 9, 15, 21, 25};
+    g.M = 0;
+    for (int m : Ms) if (32 * m >= n) { g.M = m; break; }
+    if (!g.M || (n & 3)) return false;                       // float4 path: lines are 16-B aligned
+    g.LS = 32 * g.M; g.SP = nunk * g.LS + 4;
+    const int rowf = nunk == 2 ? 7 : 4;
+    const size_t room = 227 * 1024;
+    for (int nw = kWinMaxWarps; nw >= 3; nw--) {
+        const int D = (nw + 2) / 2, R = (2 * D + nw + 9 + 7) & ~7;
+        const size_t bytes = ((size_t)R * g.SP + (size_t)nw * rowf * g.LS + R + 2 * (R / 8)) * sizeof(float);
+        if (bytes <= room) { g.NW = nw; g.R = R; g.D = D; g.smem = bytes; return true; }
+    }
+    return false;
+}
+
+template <int FAM, int DIR, int M>
+int launch_window(pdegpu_ctx *ctx, const WinParams &p, const WinGeom &g, int batch)
+{
+    static bool attr_set[16] = {false};
+    if (!attr_set[ctx->device & 15]) {
+        cudaError_t e = cudaFuncSetAttribute(alr_window_kernel<FAM, DIR, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window_kernel)");
+        attr_set[ctx->device & 15] = true;
+    }
+    const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
+    PDEGPU_PROF(ctx, DIR == 0 ? "alr_window_kernel<dir0>" : "alr_window_kernel<dir1,transposed>",
+                sweep_bytes<FAM>() * (double)p.n * p.nlines * batch);
+    alr_window_kernel<FAM, DIR, M><<<grid, g.NW * 32, g.smem, ctx->stream>>>(p);
+    PDEGPU_LAUNCH_CHECK(ctx, "alr_window_kernel");
+    return PDEGPU_OK;
+}
+
+template <int FAM, int DIR>
+int window_pass(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const xout[2], long long ostride, float omega)
+{
+    using F = Fam<FAM>;
+    WinGeom g;
+    if (!win_geometry(sys->nrows, F::NUNK, g)) return PDEGPU_ERR_UNSUPPORTED;
+    WinParams p;
+    p.s = make_view(sys);
+    p.xout[0] = xout[0]; p.xout[1] = xout[1];
+    p.ostride = ostride;
+    p.n = sys->nrows; p.nlines = sys->ncols;
+    p.NB = (sys->ncols + 7) / 8; p.TB = p.NB * sys->batch;
+    p.R = g.R; p.D = g.D;
+    p.omega = omega;
+    bool al = (sys->ncols % 4 == 0) && (ostride % 4 == 0);
+    for (int q = 0; q < F::NUNK; q++) al = al && ((uintptr_t)xout[q] % 16 == 0);
+    p.vec_ok = al ? 1 : 0;
+    switch (g.M) {
+    case 5:  return launch_window<FAM, DIR, 5>(ctx, p, g, sys->batch);
+    case 9:  return launch_window<FAM, DIR, 9>(ctx, p, g, sys->batch);
+    case 15: return launch_window<FAM, DIR, 15>(ctx, p, g, sys->batch);
+    case 21: return launch_window<FAM, DIR, 21>(ctx, p, g, sys->batch);
+    case 25: return launch_window<FAM, DIR, 25>(ctx, p, g, sys->batch);
+    default: return PDEGPU_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+int transpose_fields(pdegpu_ctx *ctx, float *dst, const float *src, int nrows, int ncols, int batch, long long sstride, long long dstride);
+
+// One ALR iteration = column pass on the problem as given (X -> XT, written transposed), then the row pass
+// as a column pass of the transposed problem (XT -> X, written transposed back). Coefficients are
+// transposed once per call.
+template <int FAM>
+static int alr_window_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    using F = Fam<FAM>;
+    if (F::PDE && F::EIGHT) return PDEGPU_ERR_UNSUPPORTED;        // interior lines only + untouched border lines: generation 1
+    WinGeom g0, g1;
+    if (!win_geometry(sys->nrows, F::NUNK, g0) || !win_geometry(sys->ncols, F::NUNK, g1)) return PDEGPU_ERR_UNSUPPORTED;
+    if (sys->nrows < 8 || sys->ncols < 8) return PDEGPU_ERR_UNSUPPORTED;
+    if ((long long)sys->batch * sys->batch_stride >= (1ll << 31)) return PDEGPU_ERR_UNSUPPORTED;
+    constexpr int NN = F::EIGHT ? 8 : 4;
+    {   // float4 loads: every field 16-B aligned, problems a multiple of 4 floats apart
+        bool al = (sys->batch_stride % 4) == 0;
+        auto a16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+        for (int n = 0; n < NN; n++) al = al && a16(sys->w[n]);
+        for (int q = 0; q < F::NUNK; q++) al = al && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]) && (!F::LATE || a16(sys->x0[q]));
+        if (F::NUNK == 2) al = al && a16(sys->m);
+        if (!al) return PDEGPU_ERR_UNSUPPORTED;
+    }
+    const long long npix = (long long)sys->nrows * sys->ncols;
+    const int nfields = NN + 3 * F::NUNK + (F::NUNK == 2 ? 1 : 0) + (F::LATE ? F::NUNK : 0);
+    int rc = pdegpu_scratch_reserve(ctx, (size_t)nfields * npix * sys->batch * sizeof(float));
+    if (rc) return rc;
+    pdegpu_system tsys = *sys;
+    float *p = (float *)ctx->scratch;
+    auto take = [&]() { float *r = p; p += npix * sys->batch; return r; };
+    auto tr = [&](const float *src) -> float * {
+        float *d = take();
+        if (!rc) rc = transpose_fields(ctx, d, src, sys->nrows, sys->ncols, sys->batch, sys->batch_stride, npix);
+        return d;
+    };
+    // neighbour roles swap under transposition: N<->W, S<->E, NE<->SW
+    static const int perm[8] = {W_N, W_W, W_S, W_E, W_NW, W_SW, W_SE, W_NE};
+    tsys.nrows = sys->ncols; tsys.ncols = sys->nrows; tsys.batch_stride = npix;
+    for (int n = 0; n < NN; n++) tsys.w[n] = tr(sys->w[perm[n]]);
+    float *xT[2] = {nullptr, nullptr};
+    for (int q = 0; q < F::NUNK; q++) {
+        tsys.c[q] = tr(sys->c[q]);
+        tsys.d[q] = tr(sys->d[q]);
+        if (F::LATE) tsys.x0[q] = tr(sys->x0[q]);
+        xT[q] = take();
+        tsys.x[q] = xT[q];
+    }
+    if (F::NUNK == 2) tsys.m = tr(sys->m);
+    if (rc) return rc;
+    float *const xN[2] = {sys->x[0], sys->x[1]};
+    for (int it = 0; it < iter; it++) {
+        if ((rc = window_pass<FAM, 0>(ctx, sys, xT, npix, omega))) return rc;
+        if ((rc = window_pass<FAM, 2>(ctx, &tsys, xN, sys->batch_stride, omega))) return rc;
+    }
+    return PDEGPU_OK;
+}
+
+int relax_window_line(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    switch (sys->family) {
+    case PDEGPU_FLOW_ELIN4: return alr_window_run<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN4: return alr_window_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN8: return alr_window_run<PDEGPU_FLOW_LLIN8>(ctx, sys, iter, omega);
+    case PDEGPU_DISP_LLIN4: return alr_window_run<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE4:       return alr_window_run<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    default: return PDEGPU_ERR_UNSUPPORTED;
+    }
+}
