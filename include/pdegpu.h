@@ -259,6 +259,93 @@ int pdegpu_dev_snd_derivatives5(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float
 int pdegpu_dev_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS,
         const float *D, int nrows, int ncols, int nframes, float eps);
 
+/* ------------------------------------------------------------------------------------------
+ * Driver-side stencils: what the reference's Matlab drivers compute between
+ * MEX calls, as device-resident entry points so that a pyramid level needs no host round trip.
+ * Device pointers, asynchronous on the context's stream. Arrays are column-major nrows x ncols
+ * (x channels); channel c of a stack starts at c*nrows*ncols.
+ * ------------------------------------------------------------------------------------------ */
+
+/* [wW wN wS wE] = OPdiffWeights(U, V)   matlab/optical_flow/FlowEminND_llin_2D_v10.m:389-433
+ * (same function in FlowEminNDFASFMG_elin_2D_v10.m:469-514). Computed in double with the reference's
+ * circshift wrap-around, stored as single (the cast the drivers apply at the MEX call). */
+int pdegpu_dev_op_diff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE,
+        const float *U, const float *V, int nrows, int ncols, int batch, long long batch_stride);
+
+/* Robust data weights + data-term assembly of the late-linearisation flow driver:
+ * products FlowEminND_llin_2D_v10.m:235-258, gD1/gD2 :289-299, nansum over channels :323-327.
+ * d1 = {I1dt, I1dx, I1dy} (channels1); d2 = {I2dt, I2dx, I2dy} or, with gradmag != 0,
+ * {I2dxt, I2dyt, I2dxx, I2dyy, I2dxy} (channels2, 0 = no second term). out = {M, Cu, Cv, Du, Dv}. */
+typedef struct pdegpu_llin_terms {
+    int nrows, ncols, batch;
+    int channels1, channels2, gradmag;
+    float b1, b2, alpha;
+    const float *d1[3];
+    const float *d2[5];
+    const float *dU, *dV;
+    float *out[5];
+    long long batch_stride1, batch_stride2, batch_stride;   /* of the d1 stacks, the d2 stacks, dU/dV/out */
+} pdegpu_llin_terms;
+int pdegpu_dev_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t);
+
+/* gd and gd-weighted terms of the FMG early-linearisation smoother:
+ * summed != 0: FlowEminNDFASFMG_elin_2D_v10.m:375-396 (gd = 1/(channels*alpha*sqrt(.)), terms summed over
+ * channels -> out[k] has one channel); summed == 0: :421-440 (gd = 1/(alpha*sqrt(.)), per-channel terms).
+ * der = {Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy}, coef = {M, Cu, Cv, Du, Dv}; gd may be NULL. */
+typedef struct pdegpu_elin_terms {
+    int nrows, ncols, channels, summed;
+    float b1, b2, alpha;
+    const float *der[8];
+    const float *coef[5];
+    const float *U, *V;
+    float *gd;
+    float *out[5];
+} pdegpu_elin_terms;
+int pdegpu_dev_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t);
+
+/* Data + symmetry terms of ONE view of the symmetric stereo driver:
+ * matlab/disparity/DispEminND_llin_sym_2D.m:172-180, 197-210, 222-225.
+ * d = {Idt, Idx, Idxt, Idyt, Idxx, Idxy} (channels). alpha_d/beta/srdiff are the driver's doubles. */
+typedef struct pdegpu_disp_sym_terms {
+    int nrows, ncols, channels;
+    float b1, b2, alpha;
+    double alpha_d, beta, srdiff;
+    const float *d[6];
+    const float *dU, *Udt, *Udx;
+    float *CuG, *DuG;
+} pdegpu_disp_sym_terms;
+int pdegpu_dev_disp_sym_terms(pdegpu_ctx *ctx, const pdegpu_disp_sym_terms *t);
+
+/* f = (R + A)./gd   FAS coarse right-hand side, FlowEminNDFASFMG_elin_2D_v10.m:250-251 */
+int pdegpu_dev_fas_rhs(pdegpu_ctx *ctx, float *f, const float *R, const float *A, const float *gd, long long n);
+
+/* out = imfilter(single(in)*prescale, h, 'replicate') (correlation; pass a flipped kernel for 'conv'),
+ * then out(1:step:end, 1:step:end). h is kr x kc, column-major, odd sizes, at most 25 taps; double
+ * accumulation. Covers the drivers' Gaussian smoothing, rgb2grad, the lpf pyramid
+ * (FlowEminNDFASFMG_elin_2D_v10.m:98,107-110) and the full-weighting restriction (:199,212-217).
+ * `planes` images, plane p at in + p*in_stride / out + p*out_stride. */
+int pdegpu_dev_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes,
+        long long in_stride, long long out_stride, const double *h, int kr, int kc, int step, float prescale);
+
+/* out = imresize(in, 'OutputSize', [out_rows out_cols], 'Method', 'bilinear') with Matlab's
+ * antialiasing when shrinking (FlowEminND_llin_2D_v10.m:107-108,365-366). `tmp` holds
+ * planes*max(in,out) pixels. scale_rows/scale_cols: the scale imresize would use (out/in, or the scalar
+ * scale argument when the driver passes one). */
+int pdegpu_dev_imresize_bilinear(pdegpu_ctx *ctx, float *out, float *tmp, const float *in,
+        int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols,
+        int antialias, int planes);
+
+/* out = medfilt2(in, [3 3], 'symmetric')  (FlowEminND_llin_2D_v10.m:354-355) */
+int pdegpu_dev_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes, long long stride);
+
+/* out = a*x + b*y in single (y may be NULL: out = a*x) */
+int pdegpu_dev_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n);
+
+/* X = meshgrid columns + U, Y = meshgrid rows + V (1-based, single): the warp coordinates the drivers
+ * hand to BilinInterp_2d (FlowEminND_llin_2D_v10.m:202,222). U/V may be NULL. */
+int pdegpu_dev_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V,
+        int nrows, int ncols, int batch, long long batch_stride);
+
 #ifdef __cplusplus
 }
 #endif

@@ -505,3 +505,101 @@ extern "C" int pdegpu_ddiff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float
     hc.fetch(wW, o[0], n); hc.fetch(wN, o[1], n); hc.fetch(wE, o[2], n); hc.fetch(wS, o[3], n);
     return hc.finish();
 }
+
+// ---------------------------------------------------------------------------------------------
+// driver-side stencils
+// ---------------------------------------------------------------------------------------------
+#define PDEGPU_ENTER(ctx)                                          \
+    if (!(ctx)) return PDEGPU_ERR_ARG;                             \
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice((ctx)->device))
+
+extern "C" int pdegpu_dev_op_diff_weights(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE,
+        const float *U, const float *V, int nrows, int ncols, int batch, long long batch_stride)
+{
+    PDEGPU_ENTER(ctx);
+    if (!wW || !wN || !wS || !wE || !U || !V || nrows < 1 || ncols < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_op_diff_weights: bad argument");
+    return op_opdiff(ctx, wW, wN, wS, wE, U, V, nrows, ncols, batch, batch_stride);
+}
+
+extern "C" int pdegpu_dev_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t)
+{
+    PDEGPU_ENTER(ctx);
+    if (!t || t->nrows < 1 || t->ncols < 1 || t->batch < 1 || t->channels1 < 1 || t->channels2 < 0) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_terms: bad argument");
+    for (int k = 0; k < 3; k++) if (!t->d1[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_terms: d1[%d] is NULL", k);
+    for (int k = 0; k < (t->channels2 ? (t->gradmag ? 5 : 3) : 0); k++) if (!t->d2[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_terms: d2[%d] is NULL", k);
+    for (int k = 0; k < 5; k++) if (!t->out[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_terms: out[%d] is NULL", k);
+    if (!t->dU || !t->dV) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_terms: dU/dV is NULL");
+    return op_llin_terms(ctx, t);
+}
+
+extern "C" int pdegpu_dev_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t)
+{
+    PDEGPU_ENTER(ctx);
+    if (!t || t->nrows < 1 || t->ncols < 1 || t->channels < 1 || !t->U || !t->V) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_elin_terms: bad argument");
+    for (int k = 0; k < 8; k++) if (!t->der[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_elin_terms: der[%d] is NULL", k);
+    for (int k = 0; k < 5; k++) if (!t->coef[k] || !t->out[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_elin_terms: coef/out[%d] is NULL", k);
+    return op_elin_terms(ctx, t);
+}
+
+extern "C" int pdegpu_dev_disp_sym_terms(pdegpu_ctx *ctx, const pdegpu_disp_sym_terms *t)
+{
+    PDEGPU_ENTER(ctx);
+    if (!t || t->nrows < 1 || t->ncols < 1 || t->channels < 1 || !t->dU || !t->Udt || !t->Udx || !t->CuG || !t->DuG) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_disp_sym_terms: bad argument");
+    for (int k = 0; k < 6; k++) if (!t->d[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_disp_sym_terms: d[%d] is NULL", k);
+    return op_disp_sym_terms(ctx, t);
+}
+
+extern "C" int pdegpu_dev_fas_rhs(pdegpu_ctx *ctx, float *f, const float *R, const float *A, const float *gd, long long n)
+{
+    PDEGPU_ENTER(ctx);
+    if (!f || !R || !A || !gd || n < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_fas_rhs: bad argument");
+    return op_fas_rhs(ctx, f, R, A, gd, n);
+}
+
+extern "C" int pdegpu_dev_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes,
+        long long in_stride, long long out_stride, const double *h, int kr, int kc, int step, float prescale)
+{
+    PDEGPU_ENTER(ctx);
+    if (!out || !in || !h || nrows < 1 || ncols < 1 || planes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_imfilter: bad argument");
+    return op_imfilter(ctx, out, in, nrows, ncols, planes, in_stride, out_stride, h, kr, kc, step, prescale);
+}
+
+extern "C" int pdegpu_dev_imresize_bilinear(pdegpu_ctx *ctx, float *out, float *tmp, const float *in,
+        int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes)
+{
+    PDEGPU_ENTER(ctx);
+    if (!out || !tmp || !in || in_rows < 1 || in_cols < 1 || out_rows < 1 || out_cols < 1 || planes < 1 || !(scale_rows > 0) || !(scale_cols > 0))
+        return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_imresize_bilinear: bad argument");
+    // imresize resizes the dimension with the smaller scale factor first (rows on a tie)
+    int rc;
+    if (scale_rows <= scale_cols) {
+        rc = op_imresize_dim(ctx, tmp, in, 0, in_rows, out_rows, in_cols, scale_rows, antialias, planes, (long long)in_rows * in_cols, (long long)out_rows * in_cols);
+        if (rc) return rc;
+        return op_imresize_dim(ctx, out, tmp, 1, in_cols, out_cols, out_rows, scale_cols, antialias, planes, (long long)out_rows * in_cols, (long long)out_rows * out_cols);
+    }
+    rc = op_imresize_dim(ctx, tmp, in, 1, in_cols, out_cols, in_rows, scale_cols, antialias, planes, (long long)in_rows * in_cols, (long long)in_rows * out_cols);
+    if (rc) return rc;
+    return op_imresize_dim(ctx, out, tmp, 0, in_rows, out_rows, out_cols, scale_rows, antialias, planes, (long long)in_rows * out_cols, (long long)out_rows * out_cols);
+}
+
+extern "C" int pdegpu_dev_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes, long long stride)
+{
+    PDEGPU_ENTER(ctx);
+    if (!out || !in || out == in || nrows < 1 || ncols < 1 || planes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_medfilt3: bad argument (out must differ from in)");
+    return op_medfilt3(ctx, out, in, nrows, ncols, planes, stride);
+}
+
+extern "C" int pdegpu_dev_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n)
+{
+    PDEGPU_ENTER(ctx);
+    if (!out || !x || n < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_axpby: bad argument");
+    return op_axpby(ctx, out, a, x, b, y, n);
+}
+
+extern "C" int pdegpu_dev_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V,
+        int nrows, int ncols, int batch, long long batch_stride)
+{
+    PDEGPU_ENTER(ctx);
+    if (!X || !Y || nrows < 1 || ncols < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_warp_coords: bad argument");
+    return op_warp_coords(ctx, X, Y, U, V, nrows, ncols, batch, batch_stride);
+}

@@ -1,0 +1,470 @@
+// driver_ops.cu -- the stencil arithmetic the reference's Matlab drivers do BETWEEN MEX calls
+// (SURVEY.md section 8a rows 17-21), as device-resident kernels so that a whole pyramid level runs
+// without host round trips:
+//
+//   op_diff_weights   OPdiffWeights            FlowEminND_llin_2D_v10.m:389-433 (= FlowEminNDFASFMG_elin_2D_v10.m:469-514)
+//   llin_terms        robust weights + terms   FlowEminND_llin_2D_v10.m:235-258, 289-299, 323-327
+//   elin_terms        FMG smoother's gd/terms  FlowEminNDFASFMG_elin_2D_v10.m:375-396, 421-440
+//   disp_sym_terms    symmetric stereo terms   DispEminND_llin_sym_2D.m:172-180, 197-210, 222-225
+//   fas_rhs           (R + A)./gd              FlowEminNDFASFMG_elin_2D_v10.m:250-251
+//   imfilter          small 2-D correlation, replicate border, optional pre-scale and decimation:
+//                     Gaussian pre-smoothing (:99,107-127), rgb2grad (:374-384), lpf pyramid
+//                     (FlowEminNDFASFMG...:98,107-110), full-weighting restriction (:199,212-217)
+//   imresize          imresize(..., 'bilinear'|'triangle') with antialiasing when shrinking
+//                     (FlowEminND_llin_2D_v10.m:107-108,365-366; FlowEminNDFASFMG...:256-257)
+//   medfilt3          medfilt2(., [3 3], 'symmetric')   (FlowEminND_llin_2D_v10.m:354-355)
+//   axpby, warp_coords   U+dU, X+U / Y+V (:202,222,228,354)
+//
+// Arithmetic follows the .m code: single where Matlab computes in single (separate roundings, no FMA
+// contraction: __fmul_rn/__fadd_rn), double where the driver casts to double or the toolbox accumulates in
+// double. The toolbox functions themselves (imresize, imfilter, medfilt2) are restated from their
+// documented behaviour: parity unpinned, checked against oracle/matlab_steps.py.
+// All kernels are streaming, HBM-bound, one thread per output pixel (fast axis = Matlab row index).
+#include "pdegpu_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int wrapi(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
+__device__ __forceinline__ int mirrori(int v, int n)            // 'symmetric' padding / imresize's index mirror
+{
+    const int p = 2 * n;
+    int m = v % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - 1 - m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// OPdiffWeights (double precision, circshift wrap) -> 4 single fields
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+op_diff_weights_kernel(float *__restrict__ wW, float *__restrict__ wN, float *__restrict__ wS, float *__restrict__ wE,
+                       const float *__restrict__ U, const float *__restrict__ V, int nr, int nc, long long stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nr) return;
+    const long long base = (long long)blockIdx.z * stride;
+    U += base; V += base;
+    auto at = [&](const float *F, int ii, int jj) -> double { return (double)F[(long long)jj * nr + ii]; };
+    // vertical / horizontal central differences [0.25 0 -0.25] (correlation, replicate border) at (ii, jj)
+    auto ver = [&](const float *F, int ii, int jj) -> double { return 0.25 * at(F, clampi(ii - 1, 0, nr - 1), jj) + (-0.25) * at(F, clampi(ii + 1, 0, nr - 1), jj); };
+    auto hor = [&](const float *F, int ii, int jj) -> double { return 0.25 * at(F, ii, clampi(jj - 1, 0, nc - 1)) + (-0.25) * at(F, ii, clampi(jj + 1, 0, nc - 1)); };
+    const int jw = wrapi(j - 1, nc), je = wrapi(j + 1, nc), in_ = wrapi(i - 1, nr), is = wrapi(i + 1, nr);
+    const double u = at(U, i, j), v = at(V, i, j);
+    const double uver = ver(U, i, j), vver = ver(V, i, j), uhor = hor(U, i, j), vhor = hor(V, i, j);
+    auto sq = [](double x) { return x * x; };
+    const double sW = sq(at(U, i, jw) - u) + sq(uver + ver(U, i, jw)) + sq(at(V, i, jw) - v) + sq(vver + ver(V, i, jw));
+    const double sE = sq(at(U, i, je) - u) + sq(uver + ver(U, i, je)) + sq(at(V, i, je) - v) + sq(vver + ver(V, i, je));
+    const double sN = sq(at(U, in_, j) - u) + sq(uhor + hor(U, in_, j)) + sq(at(V, in_, j) - v) + sq(vhor + hor(V, in_, j));
+    const double sS = sq(at(U, is, j) - u) + sq(uhor + hor(U, is, j)) + sq(at(V, is, j) - v) + sq(vhor + hor(V, is, j));
+    const long long p = base + (long long)j * nr + i;
+    wW[p] = (float)(1.0 / sqrt(sW + 0.00001));
+    wE[p] = (float)(1.0 / sqrt(sE + 0.00001));
+    wN[p] = (float)(1.0 / sqrt(sN + 0.00001));
+    wS[p] = (float)(1.0 / sqrt(sS + 0.00001));
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-precision helpers that round like Matlab / numpy (one rounding per operation)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float mulf(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addf(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subf(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float sqf(float a) { return __fmul_rn(a, a); }
+__device__ __forceinline__ float nansum_add(float acc, float t) { return is_nan(t) ? acc : __fadd_rn(acc, t); }
+
+struct LlinTermsArgs {
+    const float *d1[3];       // I1dt, I1dx, I1dy                       (c1 channels)
+    const float *d2[5];       // I2dt, I2dx, I2dy | I2dxt, I2dyt, I2dxx, I2dyy, I2dxy   (c2 channels)
+    const float *dU, *dV;
+    float *out[5];            // M, Cu, Cv, Du, Dv
+    int c1, c2, gradmag;
+    float b1, b2, alpha;
+    long long npix;           // pixels per channel
+    long long stride1, stride2, stride;   // batch strides of the d1 stacks, the d2 stacks, and of dU/dV/outputs
+};
+
+__global__ void __launch_bounds__(256)
+llin_terms_kernel(const LlinTermsArgs a)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.npix) return;
+    const long long b = blockIdx.y;
+    const float du = a.dU[b * a.stride + t], dv = a.dV[b * a.stride + t];
+    float M = 0.f, Cu = 0.f, Cv = 0.f, Du = 0.f, Dv = 0.f;
+    for (int c = 0; c < a.c1; c++) {
+        const long long p = b * a.stride1 + (long long)c * a.npix + t;
+        const float It = a.d1[0][p], Ix = a.d1[1][p], Iy = a.d1[2][p];
+        const float r = subf(subf(It, mulf(Ix, du)), mulf(Iy, dv));
+        const float g = __fdiv_rn(a.b1, mulf(a.alpha, __fsqrt_rn(addf(sqf(r), 0.00001f))));
+        M = nansum_add(M, mulf(mulf(Iy, Ix), g));
+        Cu = nansum_add(Cu, mulf(mulf(It, Ix), g));
+        Cv = nansum_add(Cv, mulf(mulf(It, Iy), g));
+        Du = nansum_add(Du, mulf(mulf(Ix, Ix), g));
+        Dv = nansum_add(Dv, mulf(mulf(Iy, Iy), g));
+    }
+    // the driver sums cat(3, X1.*gD1, X2.*gD2): all first-term channels, then all second-term channels
+    for (int c = 0; c < a.c2; c++) {
+        const long long p = b * a.stride2 + (long long)c * a.npix + t;
+        float m2, cu2, cv2, du2, dv2, op;
+        if (!a.gradmag) {
+            const float It = a.d2[0][p], Ix = a.d2[1][p], Iy = a.d2[2][p];
+            op = sqf(subf(subf(It, mulf(Ix, du)), mulf(Iy, dv)));
+            m2 = mulf(Iy, Ix); cu2 = mulf(It, Ix); cv2 = mulf(It, Iy); du2 = mulf(Ix, Ix); dv2 = mulf(Iy, Iy);
+        } else {
+            const float xt = a.d2[0][p], yt = a.d2[1][p], xx = a.d2[2][p], yy = a.d2[3][p], xy = a.d2[4][p];
+            op = addf(sqf(subf(subf(xt, mulf(xx, du)), mulf(xy, dv))), sqf(subf(subf(yt, mulf(xy, du)), mulf(yy, dv))));
+            m2 = mulf(xy, addf(xx, yy));
+            cu2 = addf(mulf(xt, xx), mulf(yt, xy));
+            cv2 = addf(mulf(xt, xy), mulf(yt, yy));
+            du2 = addf(mulf(xx, xx), mulf(xy, xy));
+            dv2 = addf(mulf(xy, xy), mulf(yy, yy));
+        }
+        const float g = __fdiv_rn(a.b2, mulf(a.alpha, __fsqrt_rn(addf(op, 0.00001f))));
+        M = nansum_add(M, mulf(m2, g)); Cu = nansum_add(Cu, mulf(cu2, g)); Cv = nansum_add(Cv, mulf(cv2, g));
+        Du = nansum_add(Du, mulf(du2, g)); Dv = nansum_add(Dv, mulf(dv2, g));
+    }
+    const long long o = b * a.stride + t;
+    a.out[0][o] = M; a.out[1][o] = Cu; a.out[2][o] = Cv; a.out[3][o] = Du; a.out[4][o] = Dv;
+}
+
+struct ElinTermsArgs {
+    const float *der[8];      // Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy   (channels)
+    const float *coef[5];     // M, Cu, Cv, Du, Dv                              (channels)
+    const float *U, *V;
+    float *gd;                // may be null; channels
+    float *out[5];            // summed: 1 channel; else channels
+    int channels, summed;
+    float b1, b2, alpha;
+    long long npix;
+};
+
+__global__ void __launch_bounds__(256)
+elin_terms_kernel(const ElinTermsArgs a)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.npix) return;
+    const float u = a.U[t], v = a.V[t];
+    const float fac = a.summed ? (float)((double)a.channels * (double)a.alpha) : a.alpha;   // channels*param.alpha is a double product, cast to single when it meets the single array
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < a.channels; c++) {
+        const long long p = (long long)c * a.npix + t;
+        const float Idt = a.der[0][p], Idx = a.der[1][p], Idy = a.der[2][p], Idxt = a.der[3][p], Idyt = a.der[4][p];
+        const float Idxx = a.der[5][p], Idyy = a.der[6][p], Idxy = a.der[7][p];
+        const float r0 = subf(subf(Idt, mulf(Idx, u)), mulf(Idy, v));
+        const float r1 = subf(subf(Idxt, mulf(Idxx, u)), mulf(Idxy, v));
+        const float r2 = subf(subf(Idyt, mulf(Idxy, u)), mulf(Idyy, v));
+        const float op = addf(mulf(a.b1, sqf(r0)), mulf(a.b2, addf(sqf(r1), sqf(r2))));
+        const float g = __fdiv_rn(1.0f, mulf(fac, __fsqrt_rn(addf(op, 0.00001f))));
+        if (a.gd) a.gd[p] = g;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float tk = mulf(a.coef[k][p], g);
+            if (a.summed) acc[k] = c == 0 ? tk : addf(acc[k], tk);
+            else a.out[k][p] = tk;
+        }
+    }
+    if (a.summed) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) a.out[k][t] = acc[k];
+    }
+}
+
+struct DispSymArgs {
+    const float *d[6];        // Idt, Idx, Idxt, Idyt, Idxx, Idxy  (channels)
+    const float *dU, *Udt, *Udx;
+    float *CuG, *DuG;
+    int channels;
+    float b1, b2, alpha, gsym_num, srdiff2;    // gsym_num = channels*beta/alpha, srdiff2 = srDiff^2 (both rounded to single like Matlab)
+    long long npix;
+};
+
+__global__ void __launch_bounds__(256)
+disp_sym_terms_kernel(const DispSymArgs a)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.npix) return;
+    const float du = a.dU[t], udt = a.Udt[t], udx = a.Udx[t];
+    float cu = 0.f, dd = 0.f;
+    for (int c = 0; c < a.channels; c++) {
+        const long long p = (long long)c * a.npix + t;
+        const float Idt = a.d[0][p], Idx = a.d[1][p], Idxt = a.d[2][p], Idyt = a.d[3][p], Idxx = a.d[4][p], Idxy = a.d[5][p];
+        const float CuD = addf(mulf(mulf(a.b1, Idt), Idx), mulf(a.b2, addf(mulf(Idxt, Idxx), mulf(Idyt, Idxy))));
+        const float DuD = addf(mulf(mulf(a.b1, Idx), Idx), mulf(a.b2, addf(mulf(Idxx, Idxx), mulf(Idxy, Idxy))));
+        const float op = addf(mulf(a.b1, sqf(subf(Idt, mulf(Idx, du)))),
+                              mulf(a.b2, addf(sqf(subf(Idxt, mulf(Idxx, du))), sqf(subf(Idyt, mulf(Idxy, du))))));
+        const float g = __fdiv_rn(1.0f, mulf(a.alpha, __fsqrt_rn(addf(op, 0.00001f))));
+        const float tc = mulf(g, CuD), td = mulf(g, DuD);
+        cu = c == 0 ? tc : addf(cu, tc);
+        dd = c == 0 ? td : addf(dd, td);
+    }
+    const float CuS = mulf(udt, addf(1.0f, udx));
+    const float DuS = addf(addf(addf(1.0f, udx), udx), mulf(udx, udx));
+    const float sn = sqf(addf(addf(du, udt), mulf(udx, du)));
+    const float gs = __fdiv_rn(a.gsym_num, addf(1.0f, __fdiv_rn(sn, a.srdiff2)));
+    a.CuG[t] = addf(cu, mulf(-gs, CuS));
+    a.DuG[t] = addf(dd, mulf(gs, DuS));
+}
+
+__global__ void __launch_bounds__(256)
+fas_rhs_kernel(float *__restrict__ f, const float *__restrict__ R, const float *__restrict__ A, const float *__restrict__ gd, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) f[t] = __fdiv_rn(addf(R[t], A[t]), gd[t]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// imfilter: correlation with a small kernel (<= 5x5), replicate border, double accumulation,
+// optional single-precision pre-scale of the input and decimation of the output
+// ---------------------------------------------------------------------------------------------
+struct FilterArgs {
+    double h[25];             // kernel, column-major like Matlab: h[b*kr + a]
+    int kr, kc;
+    int step;                 // output (i,j) = filtered (step*i, step*j)
+    float prescale;           // input is multiplied by this in single first (1 = no-op)
+    int use_prescale;
+    int nr, nc, onr, onc;
+    long long istride, ostride;   // per plane (blockIdx.z)
+};
+
+__global__ void __launch_bounds__(256)
+imfilter_kernel(float *__restrict__ out, const float *__restrict__ in, const FilterArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= a.onr) return;
+    in += (long long)blockIdx.z * a.istride;
+    const int ci = a.step * i, cj = a.step * j, cr = (a.kr - 1) >> 1, cc = (a.kc - 1) >> 1;
+    double acc = 0.0;
+    for (int ka = 0; ka < a.kr; ka++) {
+        const int ii = clampi(ci + ka - cr, 0, a.nr - 1);
+        for (int kb = 0; kb < a.kc; kb++) {
+            const double h = a.h[kb * a.kr + ka];
+            if (h == 0.0) continue;
+            const int jj = clampi(cj + kb - cc, 0, a.nc - 1);
+            float v = in[(long long)jj * a.nr + ii];
+            if (a.use_prescale) v = mulf(v, a.prescale);
+            acc += h * (double)v;
+        }
+    }
+    out[(long long)blockIdx.z * a.ostride + (long long)j * a.onr + i] = (float)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// imresize along one dimension, triangle kernel (see oracle/matlab_steps.py imresize_contributions)
+// ---------------------------------------------------------------------------------------------
+struct ResizeArgs {
+    int dim;                  // 0: along rows (fast axis), 1: along columns
+    int in_len, out_len, other;   // `other` = length of the untouched dimension
+    double scale;
+    int antialias;
+    long long istride, ostride;
+};
+
+__global__ void __launch_bounds__(256)
+imresize_kernel(float *__restrict__ out, const float *__restrict__ in, const ResizeArgs a)
+{
+    // output pixel (i, j) of an onr x onc plane
+    const int onr = a.dim == 0 ? a.out_len : a.other, inr = a.dim == 0 ? a.in_len : a.other;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= onr) return;
+    in += (long long)blockIdx.z * a.istride;
+    const bool shrink = a.scale < 1.0 && a.antialias;
+    const double kw = shrink ? 2.0 / a.scale : 2.0;
+    const int x = (a.dim == 0 ? i : j) + 1;                   // 1-based output coordinate
+    const double u = (double)x / a.scale + 0.5 * (1.0 - 1.0 / a.scale);
+    const int left = (int)floor(u - kw / 2.0);
+    const int P = (int)ceil(kw) + 2;
+    double wsum = 0.0, acc = 0.0;
+    for (int p = 0; p < P; p++) {
+        const int ind = left + p;                             // 1-based input coordinate
+        double d = u - (double)ind;
+        double w;
+        if (shrink) { d *= a.scale; w = a.scale * fmax(0.0, 1.0 - fabs(d)); }
+        else w = fmax(0.0, 1.0 - fabs(d));
+        wsum += w;
+    }
+    for (int p = 0; p < P; p++) {
+        const int ind = left + p;
+        double d = u - (double)ind;
+        double w;
+        if (shrink) { d *= a.scale; w = a.scale * fmax(0.0, 1.0 - fabs(d)); }
+        else w = fmax(0.0, 1.0 - fabs(d));
+        w /= wsum;
+        const int src = mirrori(ind - 1, a.in_len);
+        const float v = a.dim == 0 ? in[(long long)j * inr + src] : in[(long long)src * inr + i];
+        acc += w * (double)v;
+    }
+    out[(long long)blockIdx.z * a.ostride + (long long)j * onr + i] = (float)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// medfilt2(., [3 3], 'symmetric')
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cswap(float &a, float &b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+
+__global__ void __launch_bounds__(256)
+medfilt3_kernel(float *__restrict__ out, const float *__restrict__ in, int nr, int nc, long long stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nr) return;
+    in += (long long)blockIdx.z * stride;
+    float v[9];
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+            v[b * 3 + a] = in[(long long)mirrori(j + b - 1, nc) * nr + mirrori(i + a - 1, nr)];
+    // median-of-9 exchange network
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[1]); cswap(v[3], v[4]); cswap(v[6], v[7]);
+    cswap(v[1], v[2]); cswap(v[4], v[5]); cswap(v[7], v[8]);
+    cswap(v[0], v[3]); cswap(v[5], v[8]); cswap(v[4], v[7]);
+    cswap(v[3], v[6]); cswap(v[1], v[4]); cswap(v[2], v[5]);
+    cswap(v[4], v[7]); cswap(v[4], v[2]); cswap(v[6], v[4]);
+    cswap(v[4], v[2]);
+    out[(long long)blockIdx.z * stride + (long long)j * nr + i] = v[4];
+}
+
+// out = a*x + b*y (single, one rounding per operation); y may be null (b ignored)
+__global__ void __launch_bounds__(256)
+axpby_kernel(float *__restrict__ out, float a, const float *__restrict__ x, float b, const float *__restrict__ y, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float ax = a == 1.0f ? x[t] : mulf(a, x[t]);
+    out[t] = y ? addf(ax, b == 1.0f ? y[t] : mulf(b, y[t])) : ax;
+}
+
+// X = (j+1) + U, Y = (i+1) + V  (meshgrid coordinates plus flow, in single: FlowEminND_llin_2D_v10.m:202,222)
+__global__ void __launch_bounds__(256)
+warp_coords_kernel(float *__restrict__ X, float *__restrict__ Y, const float *__restrict__ U, const float *__restrict__ V, int nr, int nc, long long stride)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nr) return;
+    const long long p = (long long)blockIdx.z * stride + (long long)j * nr + i;
+    X[p] = U ? addf((float)(j + 1), U[p]) : (float)(j + 1);
+    Y[p] = V ? addf((float)(i + 1), V[p]) : (float)(i + 1);
+}
+
+inline dim3 grid2(int nr, int nc, int planes) { return dim3((nr + 255) / 256, nc, planes); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+int op_opdiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V,
+              int nr, int nc, int batch, long long stride)
+{
+    PDEGPU_PROF(ctx, "op_diff_weights_kernel", 24.0 * nr * nc * batch);
+    op_diff_weights_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(wW, wN, wS, wE, U, V, nr, nc, stride);
+    PDEGPU_LAUNCH_CHECK(ctx, "op_diff_weights_kernel");
+    return PDEGPU_OK;
+}
+
+int op_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t)
+{
+    LlinTermsArgs a;
+    for (int k = 0; k < 3; k++) a.d1[k] = t->d1[k];
+    for (int k = 0; k < 5; k++) { a.d2[k] = t->d2[k]; a.out[k] = t->out[k]; }
+    a.dU = t->dU; a.dV = t->dV;
+    a.c1 = t->channels1; a.c2 = t->channels2; a.gradmag = t->gradmag;
+    a.b1 = t->b1; a.b2 = t->b2; a.alpha = t->alpha;
+    a.npix = (long long)t->nrows * t->ncols;
+    a.stride1 = t->batch_stride1; a.stride2 = t->batch_stride2; a.stride = t->batch_stride;
+    PDEGPU_PROF(ctx, "llin_terms_kernel", 4.0 * a.npix * t->batch * (3.0 * a.c1 + (a.gradmag ? 5.0 : 3.0) * a.c2 + 7.0));
+    llin_terms_kernel<<<dim3((unsigned)((a.npix + 255) / 256), t->batch), 256, 0, ctx->stream>>>(a);
+    PDEGPU_LAUNCH_CHECK(ctx, "llin_terms_kernel");
+    return PDEGPU_OK;
+}
+
+int op_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t)
+{
+    ElinTermsArgs a;
+    for (int k = 0; k < 8; k++) a.der[k] = t->der[k];
+    for (int k = 0; k < 5; k++) { a.coef[k] = t->coef[k]; a.out[k] = t->out[k]; }
+    a.U = t->U; a.V = t->V; a.gd = t->gd;
+    a.channels = t->channels; a.summed = t->summed;
+    a.b1 = t->b1; a.b2 = t->b2; a.alpha = t->alpha;
+    a.npix = (long long)t->nrows * t->ncols;
+    PDEGPU_PROF(ctx, "elin_terms_kernel", 4.0 * a.npix * (13.0 * a.channels + 2 + (a.summed ? 5.0 : 6.0 * a.channels)));
+    elin_terms_kernel<<<(unsigned)((a.npix + 255) / 256), 256, 0, ctx->stream>>>(a);
+    PDEGPU_LAUNCH_CHECK(ctx, "elin_terms_kernel");
+    return PDEGPU_OK;
+}
+
+int op_disp_sym_terms(pdegpu_ctx *ctx, const pdegpu_disp_sym_terms *t)
+{
+    DispSymArgs a;
+    for (int k = 0; k < 6; k++) a.d[k] = t->d[k];
+    a.dU = t->dU; a.Udt = t->Udt; a.Udx = t->Udx; a.CuG = t->CuG; a.DuG = t->DuG;
+    a.channels = t->channels;
+    a.b1 = t->b1; a.b2 = t->b2; a.alpha = t->alpha;
+    a.gsym_num = (float)((double)t->channels * (double)t->beta / (double)t->alpha_d);
+    a.srdiff2 = (float)(t->srdiff * t->srdiff);
+    a.npix = (long long)t->nrows * t->ncols;
+    PDEGPU_PROF(ctx, "disp_sym_terms_kernel", 4.0 * a.npix * (6.0 * a.channels + 5));
+    disp_sym_terms_kernel<<<(unsigned)((a.npix + 255) / 256), 256, 0, ctx->stream>>>(a);
+    PDEGPU_LAUNCH_CHECK(ctx, "disp_sym_terms_kernel");
+    return PDEGPU_OK;
+}
+
+int op_fas_rhs(pdegpu_ctx *ctx, float *f, const float *R, const float *A, const float *gd, long long n)
+{
+    PDEGPU_PROF(ctx, "fas_rhs_kernel", 16.0 * n);
+    fas_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f, R, A, gd, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "fas_rhs_kernel");
+    return PDEGPU_OK;
+}
+
+int op_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long istride, long long ostride,
+                const double *h, int kr, int kc, int step, float prescale)
+{
+    if (kr < 1 || kc < 1 || kr * kc > 25 || !(kr & 1) || !(kc & 1) || step < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "imfilter: kernel must be odd-sized, at most 25 taps");
+    FilterArgs a;
+    for (int k = 0; k < kr * kc; k++) a.h[k] = h[k];
+    a.kr = kr; a.kc = kc; a.step = step; a.prescale = prescale; a.use_prescale = prescale != 1.0f;
+    a.nr = nr; a.nc = nc; a.onr = (nr + step - 1) / step; a.onc = (nc + step - 1) / step;
+    a.istride = istride; a.ostride = ostride;
+    PDEGPU_PROF(ctx, "imfilter_kernel", 4.0 * ((double)nr * nc + (double)a.onr * a.onc) * planes);
+    imfilter_kernel<<<grid2(a.onr, a.onc, planes), 256, 0, ctx->stream>>>(out, in, a);
+    PDEGPU_LAUNCH_CHECK(ctx, "imfilter_kernel");
+    return PDEGPU_OK;
+}
+
+int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int in_len, int out_len, int other, double scale,
+                    int antialias, int planes, long long istride, long long ostride)
+{
+    ResizeArgs a;
+    a.dim = dim; a.in_len = in_len; a.out_len = out_len; a.other = other; a.scale = scale; a.antialias = antialias;
+    a.istride = istride; a.ostride = ostride;
+    const int onr = dim == 0 ? out_len : other, onc = dim == 0 ? other : out_len;
+    PDEGPU_PROF(ctx, "imresize_kernel", 4.0 * ((double)in_len + out_len) * other * planes);
+    imresize_kernel<<<grid2(onr, onc, planes), 256, 0, ctx->stream>>>(out, in, a);
+    PDEGPU_LAUNCH_CHECK(ctx, "imresize_kernel");
+    return PDEGPU_OK;
+}
+
+int op_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long stride)
+{
+    PDEGPU_PROF(ctx, "medfilt3_kernel", 8.0 * nr * nc * planes);
+    medfilt3_kernel<<<grid2(nr, nc, planes), 256, 0, ctx->stream>>>(out, in, nr, nc, stride);
+    PDEGPU_LAUNCH_CHECK(ctx, "medfilt3_kernel");
+    return PDEGPU_OK;
+}
+
+int op_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n)
+{
+    PDEGPU_PROF(ctx, "axpby_kernel", (y ? 12.0 : 8.0) * n);
+    axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, a, x, b, y, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "axpby_kernel");
+    return PDEGPU_OK;
+}
+
+int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V, int nr, int nc, int batch, long long stride)
+{
+    PDEGPU_PROF(ctx, "warp_coords_kernel", 16.0 * nr * nc * batch);
+    warp_coords_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(X, Y, U, V, nr, nc, stride);
+    PDEGPU_LAUNCH_CHECK(ctx, "warp_coords_kernel");
+    return PDEGPU_OK;
+}

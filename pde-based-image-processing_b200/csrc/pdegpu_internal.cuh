@@ -122,3 +122,17 @@ int op_bilin(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, con
 int op_fst(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
 int op_snd(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
 int op_ddiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS, const float *D, int nrows, int ncols, int nframes, float eps);
+
+// driver-side stencils (driver_ops.cu)
+int op_opdiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V, int nr, int nc, int batch, long long stride);
+int op_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t);
+int op_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t);
+int op_disp_sym_terms(pdegpu_ctx *ctx, const pdegpu_disp_sym_terms *t);
+int op_fas_rhs(pdegpu_ctx *ctx, float *f, const float *R, const float *A, const float *gd, long long n);
+int op_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long istride, long long ostride,
+                const double *h, int kr, int kc, int step, float prescale);
+int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int in_len, int out_len, int other, double scale,
+                    int antialias, int planes, long long istride, long long ostride);
+int op_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long stride);
+int op_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n);
+int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V, int nr, int nc, int batch, long long stride);

@@ -33,6 +33,33 @@ class System(ctypes.Structure):
                 ("c", c_void_p * 2), ("d", c_void_p * 2), ("w", c_void_p * 8)]
 
 
+class LlinTerms(ctypes.Structure):
+    """Mirror of `pdegpu_llin_terms`."""
+    _fields_ = [("nrows", c_int), ("ncols", c_int), ("batch", c_int),
+                ("channels1", c_int), ("channels2", c_int), ("gradmag", c_int),
+                ("b1", c_float), ("b2", c_float), ("alpha", c_float),
+                ("d1", c_void_p * 3), ("d2", c_void_p * 5), ("dU", c_void_p), ("dV", c_void_p),
+                ("out", c_void_p * 5),
+                ("batch_stride1", c_longlong), ("batch_stride2", c_longlong), ("batch_stride", c_longlong)]
+
+
+class ElinTerms(ctypes.Structure):
+    """Mirror of `pdegpu_elin_terms`."""
+    _fields_ = [("nrows", c_int), ("ncols", c_int), ("channels", c_int), ("summed", c_int),
+                ("b1", c_float), ("b2", c_float), ("alpha", c_float),
+                ("der", c_void_p * 8), ("coef", c_void_p * 5), ("U", c_void_p), ("V", c_void_p),
+                ("gd", c_void_p), ("out", c_void_p * 5)]
+
+
+class DispSymTerms(ctypes.Structure):
+    """Mirror of `pdegpu_disp_sym_terms`."""
+    _fields_ = [("nrows", c_int), ("ncols", c_int), ("channels", c_int),
+                ("b1", c_float), ("b2", c_float), ("alpha", c_float),
+                ("alpha_d", ctypes.c_double), ("beta", ctypes.c_double), ("srdiff", ctypes.c_double),
+                ("d", c_void_p * 6), ("dU", c_void_p), ("Udt", c_void_p), ("Udx", c_void_p),
+                ("CuG", c_void_p), ("DuG", c_void_p)]
+
+
 _dll = None
 
 
@@ -77,6 +104,29 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_profile_enable.argtypes = [c_void_p, c_int]
         L.pdegpu_profile_report.restype = c_int
         L.pdegpu_profile_report.argtypes = [c_void_p, c_char_p, c_size_t]
+        c_double = ctypes.c_double
+        L.pdegpu_dev_op_diff_weights.restype = c_int
+        L.pdegpu_dev_op_diff_weights.argtypes = [c_void_p] + [c_void_p] * 6 + [c_int] * 3 + [c_longlong]
+        L.pdegpu_dev_llin_terms.restype = c_int
+        L.pdegpu_dev_llin_terms.argtypes = [c_void_p, POINTER(LlinTerms)]
+        L.pdegpu_dev_elin_terms.restype = c_int
+        L.pdegpu_dev_elin_terms.argtypes = [c_void_p, POINTER(ElinTerms)]
+        L.pdegpu_dev_disp_sym_terms.restype = c_int
+        L.pdegpu_dev_disp_sym_terms.argtypes = [c_void_p, POINTER(DispSymTerms)]
+        L.pdegpu_dev_fas_rhs.restype = c_int
+        L.pdegpu_dev_fas_rhs.argtypes = [c_void_p] + [c_void_p] * 4 + [c_longlong]
+        L.pdegpu_dev_imfilter.restype = c_int
+        L.pdegpu_dev_imfilter.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_longlong,
+                                          POINTER(c_double), c_int, c_int, c_int, c_float]
+        L.pdegpu_dev_imresize_bilinear.restype = c_int
+        L.pdegpu_dev_imresize_bilinear.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                                   c_double, c_double, c_int, c_int]
+        L.pdegpu_dev_medfilt3.restype = c_int
+        L.pdegpu_dev_medfilt3.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_longlong]
+        L.pdegpu_dev_axpby.restype = c_int
+        L.pdegpu_dev_axpby.argtypes = [c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p, c_longlong]
+        L.pdegpu_dev_warp_coords.restype = c_int
+        L.pdegpu_dev_warp_coords.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 3 + [c_longlong]
         L.pdegpu_upload.restype = c_int
         L.pdegpu_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
         L.pdegpu_download.restype = c_int

@@ -1,0 +1,134 @@
+"""GPU parity of the driver-side stencils against oracle/matlab_steps.py, the CPU
+restatement of the reference's .m formulas. Called through the C ABI (pdegpu_dev_*).
+
+Tolerances: formulas evaluated in single by the drivers are restated with one rounding per operation on
+both sides -> bit-exact or 1e-6; double-precision formulas cast to single -> 1e-6 relative (north_star:
+"warps and pyramids must match within 1e-6", non-iterative kernels 1e-5)."""
+import numpy as np
+import pytest
+
+from oracle import matlab_steps as ms
+from pdegpu import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def steps(built):
+    from pdegpu.steps import Steps
+    return Steps()
+
+
+def close(a, b, tol):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    return float(np.nanmax(np.abs(a - b)) / (np.nanmax(np.abs(b)) + 1e-30)) < tol
+
+
+def rnd(seed, *shape, scale=1.0):
+    return (np.random.default_rng(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (64, 48), (3, 5)])
+def test_op_diff_weights(steps, shape):
+    U, V = rnd(1, *shape), rnd(2, *shape)
+    g = steps.op_diff_weights(U, V)
+    o = ms.op_diff_weights(U, V)
+    for a, b in zip(g, o):
+        assert close(a, b.astype(np.float32), 1e-6)
+
+
+@pytest.mark.parametrize("second", ["none", "first", "gradmag"])
+@pytest.mark.parametrize("shape,c1,c2", [((37, 53), 6, 3), ((16, 24), 1, 1)])
+def test_llin_terms(steps, second, shape, c1, c2):
+    d1 = [rnd(10 + k, *shape, c1, scale=0.3) for k in range(3)]
+    d1[0][3, 4, 0] = np.nan                      # out-of-image warp -> NaN derivative -> nansum skips the channel
+    d2 = None
+    if second == "first":
+        d2 = [rnd(20 + k, *shape, c2, scale=0.3) for k in range(3)]
+    elif second == "gradmag":
+        d2 = [rnd(30 + k, *shape, c2, scale=0.3) for k in range(5)]
+        d2[2][5, 6, 0] = np.nan
+    dU, dV = rnd(40, *shape, scale=0.5), rnd(41, *shape, scale=0.5)
+    g = steps.llin_terms(d1, d2, dU, dV, 1.4843, 0.2915, 0.042, second == "gradmag")
+    o = ms.llin_terms(d1, d2, dU, dV, 1.4843, 0.2915, 0.042, second == "gradmag")
+    for a, b in zip(g, o):
+        assert close(a, b, 2e-6)
+
+
+@pytest.mark.parametrize("summed", [True, False])
+def test_elin_terms(steps, summed):
+    shape, ch = (33, 41), 3
+    der = [rnd(50 + k, *shape, ch, scale=0.2) for k in range(8)]
+    coef = [rnd(60 + k, *shape, ch, scale=0.2) for k in range(5)]
+    U, V = rnd(70, *shape), rnd(71, *shape)
+    g = steps.elin_terms(der, coef, U, V, 0.03, 0.97, 0.035, summed)
+    o = ms.elin_terms(der, coef, U, V, 0.03, 0.97, 0.035, summed)
+    for a, b in zip(g, o):
+        assert close(a, b, 2e-6)
+
+
+def test_disp_sym_terms(steps):
+    shape, ch = (29, 37), 3
+    d = [rnd(80 + k, *shape, ch, scale=0.2) for k in range(6)]
+    dU, Udt, Udx = rnd(90, *shape, scale=0.5), rnd(91, *shape, scale=0.5), rnd(92, *shape, scale=0.1)
+    g = steps.disp_sym_terms(d, dU, Udt, Udx, 0.25, 0.72, 0.035, 0.4, 1.125)
+    o = ms.disp_sym_terms(d, dU, Udt, Udx, 0.25, 0.72, 0.035, 0.4, 1.125)
+    for a, b in zip(g, o):
+        assert close(a, b, 2e-6)
+
+
+def test_fas_rhs(steps):
+    R, A = rnd(1, 21, 17, 3), rnd(2, 21, 17, 3)
+    gd = np.abs(rnd(3, 21, 17, 3)) + 0.5
+    assert np.array_equal(steps.fas_rhs(R, A, gd), ms.fas_rhs(R, A, gd))
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (480, 640), (5, 7)])
+def test_gaussian_imfilter(steps, shape):
+    A = rnd(5, *shape)
+    G = ms.fspecial_gaussian(5, 1.25)
+    assert close(steps.imfilter(A, G), ms.imfilter(A, G, "replicate"), 1e-6)
+
+
+def test_rgb2grad(steps):
+    A = rnd(6, 31, 45, 3)
+    assert close(steps.rgb2grad(A), ms.rgb2grad(A), 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (64, 48), (11, 10)])
+def test_lpf_pyramid_and_restriction(steps, shape):
+    A = rnd(7, *shape)
+    lpf = np.array([[1, 4, 6, 4, 1]], dtype=np.float64) / 16.0
+    g = steps.imfilter(steps.imfilter(A, lpf, conv=True), lpf.T, conv=True, step=2)
+    assert close(g, ms.lpf_decimate(A), 1e-6)
+    fw = np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=np.float64) / 16.0
+    g = steps.imfilter(A, fw, conv=True, step=2, prescale=0.5)
+    assert close(g, ms.fw_restrict(A, 0.5), 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (480, 640), (20, 27)])
+def test_imresize_pyramid_down_and_up(steps, shape):
+    A = rnd(8, *shape)
+    d_g, d_o = steps.imresize_bilinear(A, scale=0.75), ms.imresize_bilinear(A, scale=0.75)
+    assert d_g.shape == d_o.shape and close(d_g, d_o, 1e-6)
+    u_g, u_o = steps.imresize_bilinear(d_o, output_size=shape), ms.imresize_bilinear(d_o, output_size=shape)
+    assert close(u_g, u_o, 1e-6)
+    # FAS prolongation: factor ~2, non-integer ratio for odd sizes
+    c = rnd(9, (shape[0] + 1) // 2, (shape[1] + 1) // 2)
+    assert close(steps.imresize_bilinear(c, output_size=shape), ms.imresize_bilinear(c, output_size=shape), 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (3, 3), (128, 96)])
+def test_medfilt3(steps, shape):
+    A = rnd(10, *shape)
+    assert np.array_equal(steps.medfilt3(A), ms.medfilt2_symmetric(A))
+
+
+def test_warp_coords(steps):
+    U, V = rnd(11, 23, 31), rnd(12, 23, 31)
+    X, Y = steps.warp_coords(U, V)
+    jj, ii = np.meshgrid(np.arange(1, 32, dtype=np.float32), np.arange(1, 24, dtype=np.float32))
+    assert np.array_equal(X, jj + U) and np.array_equal(Y, ii + V)
