@@ -346,6 +346,29 @@ int pdegpu_dev_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float
 int pdegpu_dev_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V,
         int nrows, int ncols, int batch, long long batch_stride);
 
+/* ------------------------------------------------------------------------------------------
+ * Whole driver, device resident: [U V] = FlowEminND_llin_2D_v10(Iin, channels, fstTerm, sndTerm, ...)
+ * (matlab/optical_flow/FlowEminND_llin_2D_v10.m; BASELINE.json configs[1], the "640x480 flows/s" metric)
+ * for a BATCH of image pairs. I0, I1: nrows x ncols x channels per pair, values 0..255 as the driver
+ * expects (it divides by 255); pair b starts at b*nrows*ncols*channels. U, V: nrows x ncols per pair.
+ * The toolbox steps (imresize, imfilter, medfilt2) follow their documented behaviour (parity unpinned,
+ * DESIGN.md); the optional spatial a-priori inputs (param.Us/Vs) are not restated.
+ * pdegpu_dev_*: device pointers, asynchronous; pdegpu_flow_llin_2d: host pointers, H2D + D2H + sync.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pdegpu_flow_llin_params {
+    double alpha, omega, b1, b2, scl_factor;   /* 0.0420, 1.9, 1.4843, 0.2915, 0.75 (:52-62) */
+    int firstLoop, secondLoop, iter, solver;   /* 4, 4, 4, 2 */
+    int fst_grad;                              /* fstTerm: 0 'rgb', 1 'grad' */
+    int snd_term;                              /* sndTerm: 0 'none', 1 'rgb', 2 'gradmag' */
+    int max_scales;                            /* 0 = until a side is <= 20 pixels (:116) */
+    float oob_value;                           /* value of out-of-image warps (NaN) */
+} pdegpu_flow_llin_params;
+void pdegpu_flow_llin_default_params(pdegpu_flow_llin_params *p);
+int pdegpu_dev_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_llin_params *params);
+int pdegpu_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_llin_params *params);
+
 #ifdef __cplusplus
 }
 #endif

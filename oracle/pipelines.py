@@ -1,0 +1,64 @@
+"""CPU restatement of the reference's DRIVERS (matlab/*/*.m) around the MEX calls.  TEST INFRASTRUCTURE ONLY.
+
+`flow_llin` follows matlab/optical_flow/FlowEminND_llin_2D_v10.m line by line; every MEX call goes through a
+backend with the common calling convention (oracle.RefBackend = the unmodified reference C code,
+oracle.OracleBackend = the C restatement), every Matlab-side formula through oracle/matlab_steps.py.
+Toolbox steps are "parity unpinned" (see matlab_steps.py); the optional spatial a-priori inputs are omitted."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import matlab_steps as ms
+
+F32 = np.float32
+
+
+def flow_llin(I0, I1, backend, alpha=0.0420, omega=1.9, firstLoop=4, secondLoop=4, iter=4, b1=1.4843, b2=0.2915,
+              scl_factor=0.75, solver=2, fst_grad=True, snd_term="gradmag", max_scales=None, oob=np.nan):
+    """[U V] = FlowEminND_llin_2D_v10(cat(3, I0, I1), channels, fstTerm, sndTerm). I0, I1: rows x cols x channels, 0..255."""
+    I0 = (np.asarray(I0, dtype=F32).reshape(I0.shape[0], I0.shape[1], -1) / F32(255)).astype(F32)      # :73
+    I1 = (np.asarray(I1, dtype=F32).reshape(I1.shape[0], I1.shape[1], -1) / F32(255)).astype(F32)
+    G = ms.fspecial_gaussian(5, 1.25)                                                                   # :99
+    It0, It1 = [I0], [I1]
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :105-127
+        n0, n1 = ms.imresize_bilinear(It0[-1], scale=scl_factor), ms.imresize_bilinear(It1[-1], scale=scl_factor)
+        It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+        It0.append(n0); It1.append(n1)
+        if n0.shape[0] <= 20 or n0.shape[1] <= 20:
+            It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+            break
+    S = len(It0)
+    F0 = [ms.rgb2grad(x) if fst_grad else x for x in It0]                                               # :135-147
+    F1 = [ms.rgb2grad(x) if fst_grad else x for x in It1]
+    U = V = None
+    for s in range(S - 1, -1, -1):                                                                      # :195
+        rows, cols = It0[s].shape[:2]
+        Xg, Yg = np.meshgrid(np.arange(1, cols + 1, dtype=F32), np.arange(1, rows + 1, dtype=F32))
+        if U is None:
+            U = np.zeros((rows, cols), F32); V = np.zeros((rows, cols), F32)
+        for _ in range(firstLoop):                                                                      # :217
+            X, Y = (Xg + U).astype(F32), (Yg + V).astype(F32)
+            W1 = backend.bilin(F1[s], X, Y, oob)                                                        # :222
+            d1 = backend.call("FstDerivatives5", [F0[s], W1], 3)                                        # :234
+            d2 = None
+            if snd_term != "none":
+                W2 = backend.bilin(It1[s], X, Y, oob)                                                   # :228
+                d2 = backend.call("SndDerivatives5", [It0[s], W2], 5) if snd_term == "gradmag" else \
+                    backend.call("FstDerivatives5", [It0[s], W2], 3)                                    # :245,253
+            dU = np.zeros((rows, cols), F32); dV = np.zeros((rows, cols), F32)
+            for _ in range(secondLoop):                                                                 # :278
+                wW, wN, wS, wE = [w.astype(F32) for w in ms.op_diff_weights((U + dU).astype(F32), (V + dV).astype(F32))]   # :321
+                M, Cu, Cv, Du, Dv = ms.llin_terms(d1, d2, dU, dV, b1, b2, alpha, snd_term == "gradmag")  # :289-327
+                dU, dV = backend.call("Oflow_sor_llin4_2d", [U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS,
+                                                             F32(iter), F32(omega), F32(solver)], 2)    # :332-348
+            U = ms.medfilt2_symmetric((U + dU).astype(F32))                                             # :354-355
+            V = ms.medfilt2_symmetric((V + dV).astype(F32))
+        if s > 0:                                                                                       # :364-367
+            up = F32(1.0 / scl_factor)
+            size = It0[s - 1].shape[:2]
+            U = ms.imresize_bilinear((U * up).astype(F32), output_size=size)
+            V = ms.imresize_bilinear((V * up).astype(F32), output_size=size)
+    return U, V

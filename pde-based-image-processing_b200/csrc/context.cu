@@ -72,6 +72,7 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
     }
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->work) cudaFree(ctx->work);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
 }

@@ -335,6 +335,14 @@ axpby_kernel(float *__restrict__ out, float a, const float *__restrict__ x, floa
     out[t] = y ? addf(ax, b == 1.0f ? y[t] : mulf(b, y[t])) : ax;
 }
 
+// out = x / d in single (Iin = single(Iin)./255, FlowEminND_llin_2D_v10.m:73)
+__global__ void __launch_bounds__(256)
+div_kernel(float *__restrict__ out, const float *__restrict__ x, float d, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = __fdiv_rn(x[t], d);
+}
+
 // X = (j+1) + U, Y = (i+1) + V  (meshgrid coordinates plus flow, in single: FlowEminND_llin_2D_v10.m:202,222)
 __global__ void __launch_bounds__(256)
 warp_coords_kernel(float *__restrict__ X, float *__restrict__ Y, const float *__restrict__ U, const float *__restrict__ V, int nr, int nc, long long stride)
@@ -466,5 +474,13 @@ int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const fl
     PDEGPU_PROF(ctx, "warp_coords_kernel", 16.0 * nr * nc * batch);
     warp_coords_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(X, Y, U, V, nr, nc, stride);
     PDEGPU_LAUNCH_CHECK(ctx, "warp_coords_kernel");
+    return PDEGPU_OK;
+}
+
+int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long n)
+{
+    PDEGPU_PROF(ctx, "div_kernel", 8.0 * n);
+    div_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, x, d, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "div_kernel");
     return PDEGPU_OK;
 }

@@ -164,6 +164,9 @@ bilin_kernel(float *__restrict__ Iout, const float *__restrict__ Iin,
     if (i >= nrows) return;
     const long long pos = (long long)j * nrows + i;
     const long long fsz = (long long)nrows * ncols;
+    // batch of independent warps (blockIdx.z): each has its own coordinates and its own nframes images
+    X += (long long)blockIdx.z * fsz; Y += (long long)blockIdx.z * fsz;
+    Iin += (long long)blockIdx.z * fsz * nframes; Iout += (long long)blockIdx.z * fsz * nframes;
     const float Xv = X[pos], Yv = Y[pos];
     const unsigned int x = floor_to_uint_x86(SUB(Xv, 1.0f));
     const unsigned int y = floor_to_uint_x86(SUB(Yv, 1.0f));
@@ -191,9 +194,16 @@ bilin_kernel(float *__restrict__ Iout, const float *__restrict__ Iin,
 int op_bilin(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y,
              int nrows, int ncols, int nframes, float oob)
 {
+    return op_bilin_batch(ctx, Iout, Iin, X, Y, nrows, ncols, nframes, 1, oob);
+}
+
+int op_bilin_batch(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y,
+                   int nrows, int ncols, int nframes, int batch, float oob)
+{
     if (!Iout || !Iin || !X || !Y) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "bilin_interp: null pointer");
-    if (nrows < 1 || ncols < 1 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "bilin_interp: empty array");
-    dim3 block(128), grid((nrows + 127) / 128, ncols);
+    if (nrows < 1 || ncols < 1 || nframes < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "bilin_interp: empty array");
+    dim3 block(128), grid((nrows + 127) / 128, ncols, batch);
+    PDEGPU_PROF(ctx, "bilin_kernel", 4.0 * nrows * ncols * batch * (2.0 + 2.0 * nframes));
     bilin_kernel<<<grid, block, 0, ctx->stream>>>(Iout, Iin, X, Y, nrows, ncols, nframes, oob);
     PDEGPU_LAUNCH_CHECK(ctx, "bilin_kernel");
     return PDEGPU_OK;
@@ -341,6 +351,7 @@ int op_fst(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy, const float *It0
     int rc = deriv_check(ctx, nrows, ncols, nframes);
     if (rc) return rc;
     dim3 grid((nrows + DT_I - 1) / DT_I, (ncols + DT_J - 1) / DT_J, nframes);
+    PDEGPU_PROF(ctx, "deriv5_kernel<fst>", 20.0 * nrows * ncols * nframes);
     deriv5_kernel<false><<<grid, 256, 0, ctx->stream>>>(Idt, Idx, Idy, nullptr, nullptr, It0, It1, nrows, ncols);
     PDEGPU_LAUNCH_CHECK(ctx, "deriv5_kernel<fst>");
     return PDEGPU_OK;
@@ -352,6 +363,7 @@ int op_snd(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, 
     int rc = deriv_check(ctx, nrows, ncols, nframes);
     if (rc) return rc;
     dim3 grid((nrows + DT_I - 1) / DT_I, (ncols + DT_J - 1) / DT_J, nframes);
+    PDEGPU_PROF(ctx, "deriv5_kernel<snd>", 28.0 * nrows * ncols * nframes);
     deriv5_kernel<true><<<grid, 256, 0, ctx->stream>>>(Idxt, Idyt, Idxx, Idyy, Idxy, It0, It1, nrows, ncols);
     PDEGPU_LAUNCH_CHECK(ctx, "deriv5_kernel<snd>");
     return PDEGPU_OK;
@@ -423,6 +435,7 @@ int op_ddiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS, const 
     if (!wW || !wN || !wE || !wS || !D) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "ddiff_weights: null pointer");
     if (nrows < 2 || ncols < 2 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "ddiff_weights: need nrows,ncols >= 2");
     dim3 block(128), grid((nrows + 127) / 128, ncols);
+    PDEGPU_PROF(ctx, "ddiff_kernel", 4.0 * nrows * ncols * (nframes + 4.0));
     ddiff_kernel<<<grid, block, 0, ctx->stream>>>(wW, wN, wE, wS, D, nrows, ncols, nframes, eps);
     PDEGPU_LAUNCH_CHECK(ctx, "ddiff_kernel");
     return PDEGPU_OK;

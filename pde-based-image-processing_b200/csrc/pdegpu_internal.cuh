@@ -29,6 +29,9 @@ struct pdegpu_ctx {
     int           prof_on;
     int           prof_n, prof_cap;
     struct pdegpu_prof_rec *prof;
+    // workspace of the device-resident pipelines (pipeline.cu), grown on demand
+    char         *work;
+    size_t        work_bytes;
     char          err[512];
 };
 
@@ -119,6 +122,7 @@ int relax_stream(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omeg
 int op_residual(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV, bool lhs);
 int op_llin4_quirks(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV, bool lhs);
 int op_bilin(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y, int nrows, int ncols, int nframes, float oob);
+int op_bilin_batch(pdegpu_ctx *ctx, float *Iout, const float *Iin, const float *X, const float *Y, int nrows, int ncols, int nframes, int batch, float oob);
 int op_fst(pdegpu_ctx *ctx, float *Idt, float *Idx, float *Idy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
 int op_snd(pdegpu_ctx *ctx, float *Idxt, float *Idyt, float *Idxx, float *Idyy, float *Idxy, const float *It0, const float *It1, int nrows, int ncols, int nframes);
 int op_ddiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS, const float *D, int nrows, int ncols, int nframes, float eps);
@@ -136,3 +140,4 @@ int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int i
 int op_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long stride);
 int op_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n);
 int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V, int nr, int nc, int batch, long long stride);
+int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long n);
