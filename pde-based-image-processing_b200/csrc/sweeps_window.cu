@@ -39,6 +39,7 @@ struct WinParams {
     int NB, TB;            // 8-line blocks per problem, in total
     int R, D;              // ring size in lines (multiple of 8), how many pairs the even lines run ahead
     int vec_ok;            // float4 stores of X_out are aligned
+    int aligned;           // float4 loads of the inputs are aligned (else 4 scalar loads per vector)
     float omega;
 };
 
@@ -137,6 +138,14 @@ template <> struct RowF<1> { enum { A = 0, C = 1, B1 = 2, D1 = 3, B2 = 2, D2 = 3
 constexpr int kWinMaxWarps = 8;
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+// 4 consecutive elements starting at p; unaligned lines: 4 scalar loads, clamped to the `room` elements left in the line
+__device__ __forceinline__ float4 ldv(const float *p, bool aligned, int room)
+{
+    if (aligned) return ld4(p);
+    float4 v;
+    v.x = p[0]; v.y = p[min(1, room)]; v.z = p[min(2, room)]; v.w = p[min(3, room)];
+    return v;
+}
 __device__ __forceinline__ void st4(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 #define V4(v, kk) ((kk) == 0 ? (v).x : (kk) == 1 ? (v).y : (kk) == 2 ? (v).z : (v).w)
 
@@ -159,9 +168,11 @@ struct RawBatch {
     float x0Wl[NUNK], x0Wr[NUNK], x0El[NUNK], x0Er[NUNK];
 
     // ec = first element (clamped into the line), T = the line
-    __device__ __forceinline__ void issue(const SysView &s, const WinTask &T, int ec, int n)
+    __device__ __forceinline__ void issue(const SysView &s, const WinTask &T, int ec, int n, bool al)
     {
         const int ip = T.ibase + ec;
+        const int room = n - 1 - ec;                          // elements after ec that are still inside the line
+#define ld4(ptr) ldv((ptr), al, room)
         const int ipl = T.ibase + max(ec - 1, 0), ipr = T.ibase + min(ec + 4, n - 1);
         const int dW = T.dW, dE = T.dE;
 #pragma unroll
@@ -186,6 +197,7 @@ struct RawBatch {
             }
         }
         if (NUNK == 2) M4 = ld4(s.m + ip);
+#undef ld4
     }
 
     // odd lines: the unknowns at the (even) neighbour lines come from the ring of solved lines
@@ -290,13 +302,15 @@ alr_window_kernel(const WinParams p)
         T.dW = T.eW ? -n : 0; T.dE = T.eE ? n : 0;
         return true;
     };
-    auto first_element = [&](int t, int &e0, int &ec) { e0 = 128 * t + 4 * lane; ec = e0 < n ? e0 : n - 4; };
+    const int ec_last = (n - 1) & ~3;                        // first element of the last (possibly partial) vector of a line
+    const bool al = p.aligned != 0;
+    auto first_element = [&](int t, int &e0, int &ec) { e0 = 128 * t + 4 * lane; ec = min(e0, ec_last); };
 
     RawBatch<FAM> raw[2];
     WinTask cur, nxt;
     int q = warp;
     while (q < Q && !decode(q, cur)) q += nwarps;
-    if (q < Q) { int e0, ec; first_element(0, e0, ec); raw[0].issue(s, cur, ec, n); }
+    if (q < Q) { int e0, ec; first_element(0, e0, ec); raw[0].issue(s, cur, ec, n, al); }
 
     while (q < Q) {
         int q2 = q + nwarps;
@@ -318,8 +332,8 @@ alr_window_kernel(const WinParams p)
         for (int t = 0; t < NT; t++) {
             {
                 int e0n, ecn;
-                if (t + 1 < NT) { first_element(t + 1, e0n, ecn); if (e0n < LS) raw[(t + 1) & 1].issue(s, cur, ecn, n); }
-                else if (q2 < Q) { first_element(0, e0n, ecn); raw[0].issue(s, nxt, ecn, n); }
+                if (t + 1 < NT) { first_element(t + 1, e0n, ecn); if (e0n < LS) raw[(t + 1) & 1].issue(s, cur, ecn, n, al); }
+                else if (q2 < Q) { first_element(0, e0n, ecn); raw[0].issue(s, nxt, ecn, n, al); }
             }
             int e0, ec;
             first_element(t, e0, ec);
@@ -331,11 +345,11 @@ alr_window_kernel(const WinParams p)
             if (e0 < LS) {
                 RawBatch<FAM> &rb = raw[t & 1];
                 if (cur.odd) rb.neighbours_from_ring(rsW, rsE, P, ec, n);
-                const bool valid = e0 < n;
                 float ra[4], rc[4], rb1[4], rd1[4], rb2[4], rd2[4], rm[4], xo0[4], xo1[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     PixelRaw<FAM, DIR> r;
+                    const bool valid = e0 + k < n;
                     rb.template pixel<DIR>(k, ec + k, n, cur.eW, cur.eE, r);
                     float a, c, b[2], d[2], m;
                     r.rows(a, c, b, d, m);
@@ -443,7 +457,7 @@ static bool win_geometry(int n, int nunk, WinGeom &g)
     static const int Ms[] = {5, 9, 15, 21, 25};
     g.M = 0;
     for (int m : Ms) if (32 * m >= n) { g.M = m; break; }
-    if (!g.M || (n & 3)) return false;                       // float4 path: lines are 16-B aligned
+    if (!g.M || n < 8) return false;
     g.LS = 32 * g.M; g.SP = nunk * g.LS + 4;
     const int rowf = nunk == 2 ? 7 : 4;
     const size_t room = 227 * 1024;
@@ -489,6 +503,15 @@ int window_pass(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const xout[2],
     bool al = (sys->ncols % 4 == 0) && (ostride % 4 == 0);
     for (int q = 0; q < F::NUNK; q++) al = al && ((uintptr_t)xout[q] % 16 == 0);
     p.vec_ok = al ? 1 : 0;
+    {   // float4 loads need every field 16-B aligned, lines and problems a multiple of 4 floats long
+        constexpr int NN = F::EIGHT ? 8 : 4;
+        bool ia = (sys->nrows % 4 == 0) && (sys->batch_stride % 4 == 0);
+        auto a16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+        for (int n = 0; n < NN; n++) ia = ia && a16(sys->w[n]);
+        for (int q = 0; q < F::NUNK; q++) ia = ia && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]) && (!F::LATE || a16(sys->x0[q]));
+        if (F::NUNK == 2) ia = ia && a16(sys->m);
+        p.aligned = ia ? 1 : 0;
+    }
     switch (g.M) {
     case 5:  return launch_window<FAM, DIR, 5>(ctx, p, g, sys->batch);
     case 9:  return launch_window<FAM, DIR, 9>(ctx, p, g, sys->batch);
@@ -501,7 +524,30 @@ int window_pass(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const xout[2],
 
 }  // namespace
 
-int transpose_fields(pdegpu_ctx *ctx, float *dst, const float *src, int nrows, int ncols, int batch, long long sstride, long long dstride);
+// Transposes up to 16 dense column-major fields of a batch in ONE launch: dst[f][b][i*ncols + j] = src[f][b][j*nrows + i].
+struct TransposeMany { const float *src[16]; float *dst[16]; int nf; };
+
+static __global__ void __launch_bounds__(256)
+transpose_many_kernel(const TransposeMany t, int nrows, int ncols, long long sstride, long long dstride)
+{
+    __shared__ float tile[32][33];
+    const int f = blockIdx.z % t.nf, b = blockIdx.z / t.nf;
+    const float *__restrict__ src = t.src[f] + (long long)b * sstride;
+    float *__restrict__ dst = t.dst[f] + (long long)b * dstride;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + tx, j = j0 + r;
+        if (i < nrows && j < ncols) tile[r][tx] = src[(long long)j * nrows + i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int j = j0 + tx, i = i0 + r;
+        if (i < nrows && j < ncols) dst[(long long)i * ncols + j] = tile[tx][r];
+    }
+}
 
 // One ALR iteration = column pass on the problem as given (X -> XT, written transposed), then the row pass
 // as a column pass of the transposed problem (XT -> X, written transposed back). Coefficients are
@@ -514,26 +560,24 @@ static int alr_window_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, f
     WinGeom g0, g1;
     if (!win_geometry(sys->nrows, F::NUNK, g0) || !win_geometry(sys->ncols, F::NUNK, g1)) return PDEGPU_ERR_UNSUPPORTED;
     if (sys->nrows < 8 || sys->ncols < 8) return PDEGPU_ERR_UNSUPPORTED;
+    // Lines that are not a multiple of 4 floats long take 4 scalar loads per vector: measured slower than
+    // generation 1 once the problem is large enough to be bandwidth- rather than launch-bound.
+    if (((sys->nrows | sys->ncols) & 3) && (long long)sys->nrows * sys->ncols * sys->batch > (1ll << 20)) return PDEGPU_ERR_UNSUPPORTED;
     if ((long long)sys->batch * sys->batch_stride >= (1ll << 31)) return PDEGPU_ERR_UNSUPPORTED;
     constexpr int NN = F::EIGHT ? 8 : 4;
-    {   // float4 loads: every field 16-B aligned, problems a multiple of 4 floats apart
-        bool al = (sys->batch_stride % 4) == 0;
-        auto a16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
-        for (int n = 0; n < NN; n++) al = al && a16(sys->w[n]);
-        for (int q = 0; q < F::NUNK; q++) al = al && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]) && (!F::LATE || a16(sys->x0[q]));
-        if (F::NUNK == 2) al = al && a16(sys->m);
-        if (!al) return PDEGPU_ERR_UNSUPPORTED;
-    }
     const long long npix = (long long)sys->nrows * sys->ncols;
     const int nfields = NN + 3 * F::NUNK + (F::NUNK == 2 ? 1 : 0) + (F::LATE ? F::NUNK : 0);
-    int rc = pdegpu_scratch_reserve(ctx, (size_t)nfields * npix * sys->batch * sizeof(float));
+    const long long fld = (npix * sys->batch + 3) & ~3ll;      // keep every transposed field 16-B aligned
+    int rc = pdegpu_scratch_reserve(ctx, (size_t)nfields * fld * sizeof(float));
     if (rc) return rc;
     pdegpu_system tsys = *sys;
     float *p = (float *)ctx->scratch;
-    auto take = [&]() { float *r = p; p += npix * sys->batch; return r; };
+    auto take = [&]() { float *r = p; p += fld; return r; };
+    TransposeMany tm;
+    tm.nf = 0;
     auto tr = [&](const float *src) -> float * {
         float *d = take();
-        if (!rc) rc = transpose_fields(ctx, d, src, sys->nrows, sys->ncols, sys->batch, sys->batch_stride, npix);
+        tm.src[tm.nf] = src; tm.dst[tm.nf] = d; tm.nf++;
         return d;
     };
     // neighbour roles swap under transposition: N<->W, S<->E, NE<->SW
@@ -549,6 +593,13 @@ static int alr_window_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, f
         tsys.x[q] = xT[q];
     }
     if (F::NUNK == 2) tsys.m = tr(sys->m);
+    {
+        dim3 grid((sys->nrows + 31) / 32, (sys->ncols + 31) / 32, sys->batch * tm.nf);
+        if (grid.z > 65535) return PDEGPU_ERR_UNSUPPORTED;
+        PDEGPU_PROF(ctx, "transpose_many_kernel", 8.0 * npix * sys->batch * tm.nf);
+        transpose_many_kernel<<<grid, 256, 0, ctx->stream>>>(tm, sys->nrows, sys->ncols, sys->batch_stride, npix);
+        PDEGPU_LAUNCH_CHECK(ctx, "transpose_many_kernel");
+    }
     if (rc) return rc;
     float *const xN[2] = {sys->x[0], sys->x[1]};
     for (int it = 0; it < iter; it++) {
