@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--solver", type=int, default=SOLVER)
     ap.add_argument("--kernels", default="stream", choices=["stream", "simple"])
     ap.add_argument("--e2e-calls", type=int, default=4, help="host-pointer calls per e2e step")
+    ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -189,6 +190,83 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# flows/s leg: the whole configs[1] driver (FlowEminND_llin_2D_v10: 13-level pyramid, 4x4 fixed-point
+# loops, ALR iter=4) on a batch of synthetic 640x480 RGB pairs, device resident and end to end
+# ---------------------------------------------------------------------------------------------
+def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
+    import torch
+    from pdegpu import lib, synth
+    C = 3
+    L = lib.dll()
+    p = lib.FlowLlinParams()
+    L.pdegpu_flow_llin_default_params(ctypes.byref(p))
+    pairs = [synth.image_pair(100 + 7 * rank + k, NROWS, NCOLS, nframes=C, scale=255.0, max_flow=3.0) for k in range(2)]
+    h0 = np.stack([pairs[b % 2][0].reshape(-1, order="F") for b in range(FB)])
+    h1 = np.stack([pairs[b % 2][1].reshape(-1, order="F") for b in range(FB)])
+    d0, d1 = torch.from_numpy(h0).to(dev), torch.from_numpy(h1).to(dev)
+    U = torch.empty(FB, NROWS * NCOLS, device=dev)
+    V = torch.empty(FB, NROWS * NCOLS, device=dev)
+    p0, p1 = torch.from_numpy(h0).pin_memory(), torch.from_numpy(h1).pin_memory()
+    Uh, Vh = torch.empty(FB, NROWS * NCOLS).pin_memory(), torch.empty(FB, NROWS * NCOLS).pin_memory()
+
+    def dev_run():
+        ctx._chk(L.pdegpu_dev_flow_llin_2d(ctx.h, U.data_ptr(), V.data_ptr(), d0.data_ptr(), d1.data_ptr(), NROWS, NCOLS, C, FB, ctypes.byref(p)))
+
+    def host_run():
+        ctx._chk(L.pdegpu_flow_llin_2d(ctx.h, Uh.data_ptr(), Vh.data_ptr(), p0.data_ptr(), p1.data_ptr(), NROWS, NCOLS, C, FB, ctypes.byref(p)))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dev_run(); host_run()
+    barrier()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(reps):
+        dev_run()
+    ev1.record(stream)
+    barrier()
+    ms = maxr(ev0.elapsed_time(ev1)) / reps
+    launches = (ctx.launches - l0) // reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        host_run()
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0) / reps
+    u, v = pairs[0][2], pairs[0][3]
+    Ug = U[0].cpu().numpy().reshape(NROWS, NCOLS, order="F"); Vg = V[0].cpu().numpy().reshape(NROWS, NCOLS, order="F")
+    sl = (slice(8, -8), slice(8, -8))
+    aee = float(np.mean(np.sqrt((Ug[sl] - u[sl]) ** 2 + (Vg[sl] - v[sl]) ** 2)))
+    out = {"metric": "640x480 flows/s (FlowEminND_llin_2D_v10 defaults: 13 levels, firstLoop=4, secondLoop=4, ALR iter=4, 'grad'+'gradmag', RGB)",
+           "value": world * FB / (ms / 1e3), "unit": "flows/s", "batch_per_gpu": FB, "ms_per_batch": ms,
+           "gpu_launches_per_batch": int(launches), "aee_vs_ground_truth_px": aee,
+           "e2e": {"value": world * FB / e2e_s, "unit": "flows/s", "h2d_bytes_per_step": int(2 * h0.nbytes),
+                   "d2h_bytes_per_step": int(2 * FB * NROWS * NCOLS * 4), "api": "pdegpu_flow_llin_2d (host pointers, pinned)"}}
+    if rank == 0 and world == 1:
+        from oracle import oracle as orc, pipelines
+        be = orc.RefBackend() if orc.have_ref() else orc.OracleBackend()
+        t0 = time.perf_counter()
+        Uo, Vo = pipelines.flow_llin(pairs[0][0], pairs[0][1], be)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "flows/s", "cores": 1, "kind": "reference" if orc.have_ref() else "port",
+                               "sample": f"1 pair through oracle/pipelines.py (numpy restatement of the .m driver around the "
+                                         f"{be.name} MEX code), {dt:.1f} s",
+                               "aee_vs_ground_truth_px": float(np.mean(np.sqrt((Uo[sl] - u[sl]) ** 2 + (Vo[sl] - v[sl]) ** 2)))}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -296,6 +374,8 @@ def run_ours(args):
     e2e_val = world * e2e_steps * args.e2e_calls * n * ITER / 1e6 / e2e_s
     assert os.environ.get("PDEGPU_DBG") or np.isfinite(out0.numpy()).all()
 
+    flows = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_batch) if args.flow_batch > 0 else None
+
     if rank == 0:
         peak, peak_src = measured_peaks()
         top = max((p for p in prof if p["bytes_total"] > 0), key=lambda p: p["ms_total"], default=None)
@@ -325,6 +405,7 @@ def run_ours(args):
                     "calls_per_step": args.e2e_calls, "api": "pdegpu_oflow_sor_llin4_2d (host pointers, pinned)"},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "flows": flows,
             "kernels": prof,
             "clocks": clocks,
         }

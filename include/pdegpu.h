@@ -346,6 +346,16 @@ int pdegpu_dev_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float
 int pdegpu_dev_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V,
         int nrows, int ncols, int batch, long long batch_stride);
 
+/* [W NW N NE E SE S SW] = ADdiffWeights(D)   matlab/denoising/TVdenoise8.m:119-231 (Alvarez derivatives, the frame of
+ * largest gradient per pixel, lambda = the `quantile` order statistic of the non-zero squared gradient norms,
+ * found on the device). w[k] = single(scale * weight) -- the driver passes single(param.alpha*wX) to PDEsolver8
+ * (:87-100); scale = 1 gives the plain weights. If TRACE and B are not NULL the TV data terms of :83-85 are
+ * produced in the same pass, D being the current estimate Iout and Iin the noisy input (nframes each):
+ *   PsiData = 1./sqrt((Iout-Iin).^2 + eps), TRACE = PsiData + scale*(sum of the 8 weights), B = PsiData.*Iin.
+ * lambda_dev (optional): device double receiving lambda. All in double like the .m code. */
+int pdegpu_dev_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B,
+        const float *D, const float *Iin, int nrows, int ncols, int nframes, double quantile, double scale, double *lambda_dev);
+
 /* ------------------------------------------------------------------------------------------
  * Whole driver, device resident: [U V] = FlowEminND_llin_2D_v10(Iin, channels, fstTerm, sndTerm, ...)
  * (matlab/optical_flow/FlowEminND_llin_2D_v10.m; BASELINE.json configs[1], the "640x480 flows/s" metric)

@@ -317,7 +317,10 @@ def tv_terms(Iout, Iin, weights, alpha):
     Iout = np.asarray(Iout, dtype=np.float64)
     Iin = np.asarray(Iin, dtype=np.float64)
     psi = 1.0 / np.sqrt((Iout - Iin) ** 2 + np.finfo(np.float64).eps)
-    tr = psi + alpha * sum(weights)
+    sw = sum(weights)
+    if psi.ndim == 3:                      # ADdiffWeights repmat's its weights over the frames (:221-230)
+        sw = sw[:, :, None]
+    tr = psi + alpha * sw
     return tr.astype(F32), (psi * Iin).astype(F32), [np.asarray(alpha * w, dtype=F32) for w in weights]
 
 

@@ -603,3 +603,13 @@ extern "C" int pdegpu_dev_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const
     if (!X || !Y || nrows < 1 || ncols < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_warp_coords: bad argument");
     return op_warp_coords(ctx, X, Y, U, V, nrows, ncols, batch, batch_stride);
 }
+
+extern "C" int pdegpu_dev_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B,
+        const float *D, const float *Iin, int nrows, int ncols, int nframes, double quantile, double scale, double *lambda_dev)
+{
+    PDEGPU_ENTER(ctx);
+    if (!w || !D || nrows < 1 || ncols < 1 || nframes < 1 || !(quantile >= 0.0 && quantile <= 1.0)) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_ad_diff_weights: bad argument");
+    for (int k = 0; k < 8; k++) if (!w[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_ad_diff_weights: w[%d] is NULL", k);
+    if ((TRACE || B) && !(TRACE && B && Iin)) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_ad_diff_weights: TRACE, B and Iin go together");
+    return op_ad_diff_weights(ctx, w, TRACE, B, D, Iin, nrows, ncols, nframes, quantile, scale, lambda_dev);
+}

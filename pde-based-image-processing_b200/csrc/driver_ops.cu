@@ -484,3 +484,182 @@ int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long
     PDEGPU_LAUNCH_CHECK(ctx, "div_kernel");
     return PDEGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// ADdiffWeights (matlab/denoising/TVdenoise8.m:119-231): anisotropic diffusion tensor -> 8 edge weights,
+// with lambda = the `quantile` order statistic of the non-zero squared gradient norms (:196-204), found by
+// an 8-pass radix select on the device; optionally the TV data terms PsiData/TRACE/B (:83-85) in the same pass.
+// Double precision like the .m code; results cast to single as at the MEX call (:87-100).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct SelState {
+    unsigned long long prefix, k, count;
+    double lambda;
+    unsigned int hist[256];
+};
+
+// Alvarez derivatives (imfilter(D, O, 'replicate', 'conv')) of every frame, keep the frame of largest gradient norm
+__global__ void __launch_bounds__(256)
+ad_grad_kernel(double *__restrict__ mx, double *__restrict__ my, double *__restrict__ nrm, const float *__restrict__ D,
+               int nr, int nc, int frames, SelState *st)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nr) return;
+    const double s2 = sqrt(2.0), den = 4.0 + sqrt(8.0);
+    // O_dx(a,b) (row a, col b), O_dy likewise; 'conv' = correlation with the flipped kernel
+    const double odx[3][3] = {{1 / den, 0, -1 / den}, {s2 / den, 0, -s2 / den}, {1 / den, 0, -1 / den}};
+    const double ody[3][3] = {{1 / den, s2 / den, 1 / den}, {0, 0, 0}, {-1 / den, -s2 / den, -1 / den}};
+    double bx = 0, by = 0, bn = -1;
+    for (int f = 0; f < frames; f++) {
+        const float *F = D + (long long)f * nr * nc;
+        double gx = 0, gy = 0;
+        for (int a = 0; a < 3; a++) {                         // same accumulation order as oracle imfilter: rows, then columns, of the flipped kernel
+            const int ii = clampi(i + a - 1, 0, nr - 1);
+            for (int b = 0; b < 3; b++) {
+                const int jj = clampi(j + b - 1, 0, nc - 1);
+                const double v = (double)F[(long long)jj * nr + ii];
+                const double hx = odx[2 - a][2 - b], hy = ody[2 - a][2 - b];
+                if (hx != 0.0) gx = __dadd_rn(gx, __dmul_rn(hx, v));      // no FMA: lambda is an order statistic of these values
+                if (hy != 0.0) gy = __dadd_rn(gy, __dmul_rn(hy, v));
+            }
+        }
+        const double n2 = __dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy));
+        if (n2 > bn) { bn = n2; bx = gx; by = gy; }            // first maximum, like Matlab's max
+    }
+    const long long p = (long long)j * nr + i;
+    const double n2 = __dadd_rn(__dmul_rn(bx, bx), __dmul_rn(by, by));
+    mx[p] = bx; my[p] = by; nrm[p] = n2;
+    if (n2 != 0.0) atomicAdd(&st->count, 1ull);
+}
+
+__global__ void sel_init_kernel(SelState *st, double quantile)
+{
+    if (st->count == 0) { st->k = 0; st->lambda = 1.0; }
+    else {
+        double r = floor((double)st->count * quantile + 2.220446049250313e-16 + 0.5);     // Matlab round()
+        if (r < 1) r = 1;
+        if (r > (double)st->count) r = (double)st->count;
+        st->k = (unsigned long long)r;
+    }
+    st->prefix = 0;
+    for (int b = 0; b < 256; b++) st->hist[b] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+sel_hist_kernel(SelState *st, const double *__restrict__ nrm, long long n, int shift)
+{
+    __shared__ unsigned int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long prefix = st->prefix;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(nrm[t]);
+        if (key == 0) continue;
+        if (shift < 56 && (key >> (shift + 8)) != (prefix >> (shift + 8))) continue;
+        atomicAdd(&h[(key >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void sel_pick_kernel(SelState *st, int shift)
+{
+    if (st->k == 0) return;
+    unsigned long long cum = 0;
+    int b = 0;
+    for (; b < 256; b++) {
+        if (cum + st->hist[b] >= st->k) break;
+        cum += st->hist[b];
+    }
+    st->k -= cum;
+    st->prefix |= (unsigned long long)b << shift;
+    for (int q = 0; q < 256; q++) st->hist[q] = 0;
+    if (shift == 0) st->lambda = __longlong_as_double((long long)st->prefix);
+}
+
+struct AdArgs {
+    float *w[8];              // W, NW, N, NE, E, SE, S, SW  (scaled by `scale`)
+    float *TRACE, *B;         // optional (frames each)
+    const float *Iout, *Iin;  // for TRACE/B
+    const double *mx, *my, *nrm;
+    const SelState *st;
+    int nr, nc, frames;
+    double scale;
+};
+
+__global__ void __launch_bounds__(256)
+ad_weights_kernel(const AdArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= a.nr) return;
+    const int nr = a.nr, nc = a.nc;
+    const double lam = a.st->lambda;
+    auto tensor = [&](int ii, int jj, double &dyy, double &dxx, double &dxy) {
+        const long long p = (long long)wrapi(jj, nc) * nr + wrapi(ii, nr);     // circshift wraps; wrapped values are zeroed below
+        const double x = a.mx[p], y = a.my[p];
+        const double mul = 1.0 / (a.nrm[p] + 2 * lam);
+        dyy = mul * (y * y + lam); dxx = mul * (x * x + lam); dxy = -mul * (x * y);
+    };
+    double cyy, cxx, cxy, tyy, txx, txy;
+    tensor(i, j, cyy, cxx, cxy);
+    double w[8];
+    tensor(i, j - 1, tyy, txx, txy);      w[0] = j == 0 ? 0.0 : 0.5 * (cyy + tyy);                                // W
+    tensor(i - 1, j - 1, tyy, txx, txy);  w[1] = (j == 0 || i == 0) ? 0.0 : 0.25 * (cxy + txy);                   // NW
+    tensor(i - 1, j, tyy, txx, txy);      w[2] = i == 0 ? 0.0 : 0.5 * (cxx + txx);                                // N
+    tensor(i - 1, j + 1, tyy, txx, txy);  w[3] = (j == nc - 1 || i == 0) ? 0.0 : -0.25 * (cxy + txy);             // NE
+    tensor(i, j + 1, tyy, txx, txy);      w[4] = j == nc - 1 ? 0.0 : 0.5 * (cyy + tyy);                           // E
+    tensor(i + 1, j + 1, tyy, txx, txy);  w[5] = (j == nc - 1 || i == nr - 1) ? 0.0 : 0.25 * (cxy + txy);         // SE
+    tensor(i + 1, j, tyy, txx, txy);      w[6] = i == nr - 1 ? 0.0 : 0.5 * (cxx + txx);                           // S
+    tensor(i + 1, j - 1, tyy, txx, txy);  w[7] = (i == nr - 1 || j == 0) ? 0.0 : -0.25 * (cxy + txy);             // SW
+    const long long p = (long long)j * nr + i;
+#pragma unroll
+    for (int k = 0; k < 8; k++) a.w[k][p] = (float)(a.scale * w[k]);
+    if (a.TRACE) {
+        const double sw = ((((((w[0] + w[1]) + w[2]) + w[3]) + w[4]) + w[5]) + w[6]) + w[7];
+        for (int f = 0; f < a.frames; f++) {
+            const long long q = (long long)f * nr * nc + p;
+            const double io = (double)a.Iout[q], ii = (double)a.Iin[q];
+            const double psi = 1.0 / sqrt((io - ii) * (io - ii) + 2.220446049250313e-16);
+            a.TRACE[q] = (float)(psi + a.scale * sw);
+            a.B[q] = (float)(psi * ii);
+        }
+    }
+}
+
+}  // namespace
+
+int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin,
+                       int nr, int nc, int frames, double quantile, double scale, double *lambda_dev)
+{
+    const long long n = (long long)nr * nc;
+    const size_t need = 3 * n * sizeof(double) + sizeof(SelState) + 256;
+    int rc = pdegpu_scratch_reserve(ctx, need);
+    if (rc) return rc;
+    double *mx = (double *)ctx->scratch, *my = mx + n, *nrm = my + n;
+    SelState *st = (SelState *)(nrm + n);
+    PDEGPU_CUDA_OK(ctx, cudaMemsetAsync(st, 0, sizeof(SelState), ctx->stream));
+    PDEGPU_PROF(ctx, "ad_grad_kernel", (4.0 * frames + 24.0) * n);
+    ad_grad_kernel<<<grid2(nr, nc, 1), 256, 0, ctx->stream>>>(mx, my, nrm, D, nr, nc, frames, st);
+    PDEGPU_LAUNCH_CHECK(ctx, "ad_grad_kernel");
+    sel_init_kernel<<<1, 1, 0, ctx->stream>>>(st, quantile);
+    PDEGPU_LAUNCH_CHECK(ctx, "sel_init_kernel");
+    const int blocks = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        PDEGPU_PROF(ctx, "sel_hist_kernel", 8.0 * n);
+        sel_hist_kernel<<<blocks, 256, 0, ctx->stream>>>(st, nrm, n, shift);
+        PDEGPU_LAUNCH_CHECK(ctx, "sel_hist_kernel");
+        sel_pick_kernel<<<1, 1, 0, ctx->stream>>>(st, shift);
+        PDEGPU_LAUNCH_CHECK(ctx, "sel_pick_kernel");
+    }
+    AdArgs a;
+    for (int k = 0; k < 8; k++) a.w[k] = w[k];
+    a.TRACE = TRACE; a.B = B; a.Iout = D; a.Iin = Iin;
+    a.mx = mx; a.my = my; a.nrm = nrm; a.st = st;
+    a.nr = nr; a.nc = nc; a.frames = frames; a.scale = scale;
+    PDEGPU_PROF(ctx, "ad_weights_kernel", (24.0 + 32.0 + (TRACE ? 16.0 * frames : 0.0)) * n);
+    ad_weights_kernel<<<grid2(nr, nc, 1), 256, 0, ctx->stream>>>(a);
+    PDEGPU_LAUNCH_CHECK(ctx, "ad_weights_kernel");
+    if (lambda_dev) PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(lambda_dev, &st->lambda, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PDEGPU_OK;
+}

@@ -135,6 +135,9 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_dev_axpby.argtypes = [c_void_p, c_void_p, c_float, c_void_p, c_float, c_void_p, c_longlong]
         L.pdegpu_dev_warp_coords.restype = c_int
         L.pdegpu_dev_warp_coords.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 3 + [c_longlong]
+        L.pdegpu_dev_ad_diff_weights.restype = c_int
+        L.pdegpu_dev_ad_diff_weights.argtypes = [c_void_p, POINTER(c_void_p * 8), c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_int, c_int, c_int, c_double, c_double, c_void_p]
         L.pdegpu_flow_llin_default_params.restype = None
         L.pdegpu_flow_llin_default_params.argtypes = [POINTER(FlowLlinParams)]
         for fn in (L.pdegpu_dev_flow_llin_2d, L.pdegpu_flow_llin_2d):

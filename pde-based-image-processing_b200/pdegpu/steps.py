@@ -165,6 +165,28 @@ class Steps:
         self._run(self.L.pdegpu_dev_warp_coords(self.ctx.h, x.data_ptr(), y.data_ptr(), u.data_ptr(), v.data_ptr(), nr, nc, 1, nr * nc))
         return _host(x, (nr, nc)), _host(y, (nr, nc))
 
+    def ad_diff_weights(self, D, Iin=None, quantile=0.5, scale=1.0):
+        """(W, NW, N, NE, E, SE, S, SW, lambda[, TRACE, B])"""
+        import torch
+        D = np.asarray(D, dtype=np.float32)
+        D3 = D.reshape(D.shape[0], D.shape[1], -1)
+        nr, nc, fr = D3.shape
+        d = _dev(D3)
+        w = [_empty(nr * nc) for _ in range(8)]
+        arr = (ctypes.c_void_p * 8)(*[t.data_ptr() for t in w])
+        lam = torch.zeros(1, dtype=torch.float64, device="cuda:0")
+        tr = bb = iin = None
+        if Iin is not None:
+            iin = _dev(np.asarray(Iin, dtype=np.float32).reshape(nr, nc, fr))
+            tr, bb = _empty(nr * nc * fr), _empty(nr * nc * fr)
+        self._run(self.L.pdegpu_dev_ad_diff_weights(self.ctx.h, ctypes.byref(arr), tr.data_ptr() if tr is not None else None,
+                                                    bb.data_ptr() if bb is not None else None, d.data_ptr(),
+                                                    iin.data_ptr() if iin is not None else None, nr, nc, fr, quantile, scale, lam.data_ptr()))
+        out = tuple(_host(t, (nr, nc)) for t in w) + (float(lam.item()),)
+        if tr is not None:
+            out += (_host(tr, D.shape), _host(bb, D.shape))
+        return out
+
     def rgb2grad(self, IN):
         IN = np.asarray(IN, dtype=np.float32).reshape(IN.shape[0], IN.shape[1], -1)
         out = np.zeros(IN.shape[:2] + (2 * IN.shape[2],), dtype=np.float32)

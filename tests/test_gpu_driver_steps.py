@@ -132,3 +132,24 @@ def test_warp_coords(steps):
     X, Y = steps.warp_coords(U, V)
     jj, ii = np.meshgrid(np.arange(1, 32, dtype=np.float32), np.arange(1, 24, dtype=np.float32))
     assert np.array_equal(X, jj + U) and np.array_equal(Y, ii + V)
+
+
+@pytest.mark.parametrize("shape,frames", [((37, 53), 1), ((64, 48), 3), ((120, 160), 1)])
+def test_ad_diff_weights_and_tv_terms(steps, shape, frames):
+    """ADdiffWeights incl. the device-side quantile select, and the TV data terms (TVdenoise8.m:83-85,119-231)."""
+    D = np.abs(rnd(13, *shape, frames, scale=0.3)) + 0.2
+    D[5:9, 7:12] = 0.5                                          # a flat patch: zero gradients are excluded from the quantile
+    Iin = (D + rnd(14, *shape, frames, scale=0.05)).astype(np.float32)
+    if frames == 1:
+        D, Iin = D[:, :, 0], Iin[:, :, 0]
+    alpha = 500.0
+    o = ms.ad_diff_weights(D)
+    g = steps.ad_diff_weights(D, Iin=Iin, scale=alpha)
+    assert abs(g[8] - o[8]) <= 1e-12 * o[8], f"lambda {g[8]} vs {o[8]}"
+    tr, b, ws = ms.tv_terms(D, Iin, o[:8], alpha)
+    for k in range(8):
+        assert close(g[k], ws[k], 1e-6)
+    assert close(g[9], tr, 1e-6) and close(g[10], b, 1e-6)
+    g1 = steps.ad_diff_weights(D)
+    for k in range(8):
+        assert close(g1[k], o[k].astype(np.float32), 1e-6)
