@@ -21,21 +21,68 @@
 // ---------------------------------------------------------------------------------------------
 // point update (interior pixels only: all neighbours exist)
 // ---------------------------------------------------------------------------------------------
+// One SOR point update from VALUES (4-neighbour stencils): w = {wW, wN, wE, wS}, xn[q][n] the unknown q at
+// neighbour n (same order), xc[q] at the pixel, x0n/x0c the fixed fields of the late-linearisation families.
+// Shared by the global-memory kernel (point_update) and the tiled kernel (sweeps_point.cu) so that both
+// evaluate the same expressions.
+template <int FAM>
+__device__ __forceinline__ void point_formula(const float (&w)[4], const float (&xn)[2][4], const float (&xc)[2],
+                                              const float (&x0n)[2][4], const float (&x0c)[2],
+                                              const float (&C)[2], const float (&D)[2], float M, float omega, float (&out)[2])
+{
+    using F = Fam<FAM>;
+    const float wW = w[W_W], wN = w[W_N], wE = w[W_E], wS = w[W_S];
+    const float sw = (wW + wE) + (wN + wS);
+    if (F::PDE) {
+        const float nb = xn[0][W_E] * wE + xn[0][W_W] * wW + xn[0][W_S] * wS + xn[0][W_N] * wN;
+        const float tr = D[0];
+        float inv, bt;
+        if (!is_nan(tr)) { inv = 1.0f / tr; bt = C[0]; }
+        else             { inv = 1.0f / sw; bt = 0.0f; }
+        out[0] = (1.0f - omega) * xc[0] + omega * (bt + nb) * inv;
+        return;
+    }
+    float nb[2];
+#pragma unroll
+    for (int q = 0; q < F::NUNK; q++) {
+        if (F::LATE) {
+            const float c0 = x0c[q];
+            nb[q] = (xn[q][W_W] + x0n[q][W_W] - c0) * wW + (xn[q][W_E] + x0n[q][W_E] - c0) * wE
+                  + (xn[q][W_N] + x0n[q][W_N] - c0) * wN + (xn[q][W_S] + x0n[q][W_S] - c0) * wS;
+        } else {
+            nb[q] = xn[q][W_W] * wW + xn[q][W_E] * wE + xn[q][W_N] * wN + xn[q][W_S] * wS;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < F::NUNK; q++) {
+        float inv, val;
+        if (F::NUNK == 2) {
+            // flow: divisor tests isnan(D), right-hand side tests isnan(C) (opticalflowSolvers.c:118-149)
+            inv = 1.0f / (is_nan(D[q]) ? sw : sw + D[q]);
+            val = is_nan(C[q]) ? nb[q] : (nb[q] + C[q] - M * xc[1 - q]);
+        } else {
+            // disparity: both test isnan(Cu) (disparitySolvers.c:96-112)
+            const bool t = !is_nan(C[q]);
+            inv = 1.0f / (t ? (D[q] + sw) : sw);
+            val = t ? (nb[q] + C[q]) : nb[q];
+        }
+        out[q] = (1.0f - omega) * xc[q] + omega * (val * inv);
+    }
+}
+
 template <int FAM>
 __device__ __forceinline__ void point_update(const SysView &s, long long pos, float omega)
 {
     using F = Fam<FAM>;
     const int nr = s.nrows;
-    const float wW = s.w[W_W][pos], wN = s.w[W_N][pos], wE = s.w[W_E][pos], wS = s.w[W_S][pos];
-    float sw = (wW + wE) + (wN + wS);
-    if (F::PDE) {
+    if (F::PDE && F::EIGHT) {
+        const float wW = s.w[W_W][pos], wN = s.w[W_N][pos], wE = s.w[W_E][pos], wS = s.w[W_S][pos];
+        float sw = (wW + wE) + (wN + wS);
         float *X = s.x[0];
         float nb = X[pos + nr] * wE + X[pos - nr] * wW + X[pos + 1] * wS + X[pos - 1] * wN;
-        if (F::EIGHT) {
-            const float wNW = s.w[W_NW][pos], wNE = s.w[W_NE][pos], wSE = s.w[W_SE][pos], wSW = s.w[W_SW][pos];
-            nb += X[pos - nr + 1] * wSW + X[pos - nr - 1] * wNW + X[pos + nr + 1] * wSE + X[pos + nr - 1] * wNE;
-            sw += (wSW + wNW) + (wSE + wNE);
-        }
+        const float wNW = s.w[W_NW][pos], wNE = s.w[W_NE][pos], wSE = s.w[W_SE][pos], wSW = s.w[W_SW][pos];
+        nb += X[pos - nr + 1] * wSW + X[pos - nr - 1] * wNW + X[pos + nr + 1] * wSE + X[pos + nr - 1] * wNE;
+        sw += (wSW + wNW) + (wSE + wNE);
         const float tr = s.d[0][pos];
         float inv, bt;
         if (!is_nan(tr)) { inv = 1.0f / tr; bt = s.c[0][pos]; }
@@ -43,38 +90,27 @@ __device__ __forceinline__ void point_update(const SysView &s, long long pos, fl
         X[pos] = (1.0f - omega) * X[pos] + omega * (bt + nb) * inv;
         return;
     }
-    // flow / disparity families; the 8-neighbour flow point solver ignores its diagonal weights
+    // flow / disparity / 4-neighbour PDE; the 8-neighbour flow point solver ignores its diagonal weights
     // (GS_SOR_llin8_2d opticalflowSolvers.c:1550-1598) => identical to llin4.
-    float nb[2], xc[2];
+    const long long off[4] = {-(long long)nr, -1, (long long)nr, 1};
+    float w[4], xn[2][4], xc[2], x0n[2][4], x0c[2], C[2], D[2], out[2];
+#pragma unroll
+    for (int n = 0; n < 4; n++) w[n] = s.w[n][pos];
 #pragma unroll
     for (int q = 0; q < F::NUNK; q++) {
-        const float *X = s.x[q];
-        xc[q] = X[pos];
-        if (F::LATE) {
-            const float *X0 = s.x0[q];
-            const float c0 = X0[pos];
-            nb[q] = (X[pos - nr] + X0[pos - nr] - c0) * wW + (X[pos + nr] + X0[pos + nr] - c0) * wE
-                  + (X[pos - 1] + X0[pos - 1] - c0) * wN + (X[pos + 1] + X0[pos + 1] - c0) * wS;
-        } else {
-            nb[q] = X[pos - nr] * wW + X[pos + nr] * wE + X[pos - 1] * wN + X[pos + 1] * wS;
-        }
-    }
+        xc[q] = s.x[q][pos];
+        C[q] = s.c[q][pos]; D[q] = s.d[q][pos];
+        if (F::LATE) x0c[q] = s.x0[q][pos];
 #pragma unroll
-    for (int q = 0; q < F::NUNK; q++) {
-        const float C = s.c[q][pos], D = s.d[q][pos];
-        float inv, val;
-        if (F::NUNK == 2) {
-            // flow: divisor tests isnan(D), right-hand side tests isnan(C) (opticalflowSolvers.c:118-149)
-            inv = 1.0f / (is_nan(D) ? sw : sw + D);
-            val = is_nan(C) ? nb[q] : (nb[q] + C - s.m[pos] * xc[1 - q]);
-        } else {
-            // disparity: both test isnan(Cu) (disparitySolvers.c:96-112)
-            const bool t = !is_nan(C);
-            inv = 1.0f / (t ? (D + sw) : sw);
-            val = t ? (nb[q] + C) : nb[q];
+        for (int n = 0; n < 4; n++) {
+            xn[q][n] = s.x[q][pos + off[n]];
+            if (F::LATE) x0n[q][n] = s.x0[q][pos + off[n]];
         }
-        s.x[q][pos] = (1.0f - omega) * xc[q] + omega * (val * inv);
     }
+    const float M = F::NUNK == 2 ? s.m[pos] : 0.0f;
+    point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, M, omega, out);
+#pragma unroll
+    for (int q = 0; q < F::NUNK; q++) s.x[q][pos] = out[q];
 }
 
 // ---------------------------------------------------------------------------------------------

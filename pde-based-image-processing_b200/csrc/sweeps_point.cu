@@ -1,8 +1,210 @@
-// sweeps_point.cu -- kernel generation 1, solver 1 (placeholder: not implemented yet).
+// sweeps_point.cu -- kernel generation 1, solver 1: red-black point SOR, one launch per full sweep.
+//
+// Generation 0 runs one launch per colour; each of them drags every coefficient sector through the SMs and
+// uses half of it. Here a CTA owns a 128 x 8 tile (fast axis = Matlab row index i) and does the whole sweep
+// on it:
+//   1. the unknowns (and the fixed U,V of the late-linearisation families) of the tile plus a 2-pixel halo go
+//      to shared memory; every thread loads the coefficients of its own 4 consecutive pixels ONCE (float4);
+//   2. red half-sweep on the tile plus a 1-pixel ring (the ring's red pixels are recomputed here so that the
+//      black pixels on the tile edge see new red values without any inter-CTA synchronisation);
+//   3. black half-sweep on the tile;
+//   4. the tile goes to X_out. The sweep is out of place (neighbouring CTAs read old values from X_in), the
+//      two arrays swap roles from sweep to sweep, and the reference's border fill (opticalflowSolvers.c:161-179)
+//      runs as generation 0's border kernel on X_out.
+// HBM traffic per sweep = algorithmic (every field once, unknowns written once) plus the halo re-reads, which
+// hit L2. Same ordering and the same arithmetic (point_formula) as generation 0.
 #include "stencil_math.cuh"
+#include <stdlib.h>
+
+namespace {
+
+constexpr int PT_I = 128, PT_J = 8, PT_H = 2;                 // tile and halo
+constexpr int PS_I = PT_I + 2 * PT_H, PS_J = PT_J + 2 * PT_H; // shared-memory extent
+constexpr int PS_P = PS_I + 1;                                // pitch
+
+template <int FAM>
+__global__ void __launch_bounds__(256)
+rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega, int aligned)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK;
+    constexpr int NF = NUNK * (F::LATE ? 2 : 1);              // fields kept in shared memory: x[q], then x0[q]
+    __shared__ float sm[NF][PS_J][PS_P];
+    const int nr = s.nrows, nc = s.ncols;
+    const int i0 = blockIdx.x * PT_I, j0 = blockIdx.y * PT_J;
+    const long long base = (long long)blockIdx.z * s.bstride;
+    const int tid = threadIdx.x;
+    const float *fld[4] = {s.x[0] + base, NUNK == 2 ? s.x[1] + base : nullptr,
+                           F::LATE ? s.x0[0] + base : nullptr, (F::LATE && NUNK == 2) ? s.x0[1] + base : nullptr};
+    // 1. unknowns + halo (indices clamped into the image: clamped copies are never used by an interior update)
+    for (int t = tid; t < PS_I * PS_J; t += 256) {
+        const int li = t % PS_I, lj = t / PS_I;
+        const int gi = min(max(i0 + li - PT_H, 0), nr - 1), gj = min(max(j0 + lj - PT_H, 0), nc - 1);
+        const long long p = (long long)gj * nr + gi;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            sm[q][lj][li] = fld[q][p];
+            if (F::LATE) sm[NUNK + q][lj][li] = fld[2 + (NUNK == 2 ? q : 0)][p];
+        }
+    }
+    // coefficients of this thread's 4 pixels
+    const int ti = (tid & 31) * 4, tj = tid >> 5;
+    const int gi0 = i0 + ti, gj = j0 + tj;
+    float4 w4[4], C4[2], D4[2], M4;
+    const bool row_ok = gj < nc && gi0 < nr;
+    {
+        const long long p = base + (long long)min(gj, nc - 1) * nr + min(gi0, nr - 1);
+        const int room = nr - 1 - min(gi0, nr - 1);
+        auto ldv = [&](const float *f) -> float4 {
+            if (aligned && room >= 3) return *reinterpret_cast<const float4 *>(f + p);
+            float4 v;
+            v.x = f[p]; v.y = f[p + min(1, room)]; v.z = f[p + min(2, room)]; v.w = f[p + min(3, room)];
+            return v;
+        };
+#pragma unroll
+        for (int n = 0; n < 4; n++) w4[n] = ldv(s.w[n]);
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) { C4[q] = ldv(s.c[q]); D4[q] = ldv(s.d[q]); }
+        if (NUNK == 2) M4 = ldv(s.m);
+    }
+    __syncthreads();
+
+    // update of the pixel at shared-memory position (li, lj) from given coefficients
+    auto update = [&](int li, int lj, const float (&w)[4], const float (&C)[2], const float (&D)[2], float M) {
+        float xn[2][4], xc[2], x0n[2][4], x0c[2], out[2];
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            xc[q] = sm[q][lj][li];
+            xn[q][W_W] = sm[q][lj - 1][li]; xn[q][W_E] = sm[q][lj + 1][li];
+            xn[q][W_N] = sm[q][lj][li - 1]; xn[q][W_S] = sm[q][lj][li + 1];
+            if (F::LATE) {
+                x0c[q] = sm[NUNK + q][lj][li];
+                x0n[q][W_W] = sm[NUNK + q][lj - 1][li]; x0n[q][W_E] = sm[NUNK + q][lj + 1][li];
+                x0n[q][W_N] = sm[NUNK + q][lj][li - 1]; x0n[q][W_S] = sm[NUNK + q][lj][li + 1];
+            }
+        }
+        point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, M, omega, out);
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) sm[q][lj][li] = out[q];
+    };
+    auto own = [&](int colour) {
+        if (!row_ok || gj < 1 || gj > nc - 2) return;
+#define V4(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gi = gi0 + k;
+            if (gi < 1 || gi > nr - 2 || ((gi + gj) & 1) != colour) continue;
+            const float w[4] = {V4(w4[0], k), V4(w4[1], k), V4(w4[2], k), V4(w4[3], k)};
+            const float C[2] = {V4(C4[0], k), NUNK == 2 ? V4(C4[NUNK - 1], k) : 0.f};
+            const float D[2] = {V4(D4[0], k), NUNK == 2 ? V4(D4[NUNK - 1], k) : 0.f};
+            update(ti + k + PT_H, tj + PT_H, w, C, D, NUNK == 2 ? V4(M4, k) : 0.f);
+        }
+#undef V4
+    };
+    // 2. red: own pixels, then the red pixels of the 1-pixel ring around the tile
+    own(0);
+    {
+        constexpr int RING = 2 * (PT_I + 2) + 2 * PT_J;
+        for (int t = tid; t < RING; t += 256) {
+            int li, lj;                                       // position in the (PT_I+2) x (PT_J+2) frame, origin = tile - 1
+            if (t < PT_I + 2) { li = t; lj = 0; }
+            else if (t < 2 * (PT_I + 2)) { li = t - (PT_I + 2); lj = PT_J + 1; }
+            else if (t < 2 * (PT_I + 2) + PT_J) { li = 0; lj = 1 + t - 2 * (PT_I + 2); }
+            else { li = PT_I + 1; lj = 1 + t - 2 * (PT_I + 2) - PT_J; }
+            const int gi = i0 + li - 1, gjr = j0 + lj - 1;
+            if (gi < 1 || gi > nr - 2 || gjr < 1 || gjr > nc - 2 || ((gi + gjr) & 1) != 0) continue;
+            const long long p = base + (long long)gjr * nr + gi;
+            const float w[4] = {s.w[0][p], s.w[1][p], s.w[2][p], s.w[3][p]};
+            const float C[2] = {s.c[0][p], NUNK == 2 ? s.c[NUNK - 1][p] : 0.f};
+            const float D[2] = {s.d[0][p], NUNK == 2 ? s.d[NUNK - 1][p] : 0.f};
+            update(li + PT_H - 1, lj + PT_H - 1, w, C, D, NUNK == 2 ? s.m[p] : 0.f);
+        }
+    }
+    __syncthreads();
+    // 3. black
+    own(1);
+    // 4. own pixels -> X_out (each thread wrote its own pixels last: no barrier needed)
+    if (row_ok) {
+        float *xo[2] = {xo0 + base, NUNK == 2 ? xo1 + base : nullptr};
+        const long long p = (long long)gj * nr + gi0;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            const float *r = &sm[q][tj + PT_H][ti + PT_H];
+            if (aligned && gi0 + 3 < nr) *reinterpret_cast<float4 *>(xo[q] + p) = make_float4(r[0], r[1], r[2], r[3]);
+            else for (int k = 0; k < 4 && gi0 + k < nr; k++) xo[q][p + k] = r[k];
+        }
+    }
+}
+
+template <int NUNK>
+__global__ void border_fill_tile_kernel(float *x0, float *x1, int nr, int nc, long long bstride)
+{
+    // border pixel := nearest interior pixel (rows first, then columns: corners take the diagonal neighbour)
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 2 * nr + 2 * nc;
+    if (t >= per) return;
+    int i, j;
+    if (t < nr)               { i = t;            j = 0; }
+    else if (t < 2 * nr)      { i = t - nr;       j = nc - 1; }
+    else if (t < 2 * nr + nc) { i = 0;            j = t - 2 * nr; }
+    else                      { i = nr - 1;       j = t - 2 * nr - nc; }
+    const int ic = min(max(i, 1), nr - 2), jc = min(max(j, 1), nc - 2);
+    const long long base = (long long)blockIdx.y * bstride;
+    float *x[2] = {x0, x1};
+#pragma unroll
+    for (int q = 0; q < NUNK; q++) x[q][base + (long long)j * nr + i] = x[q][base + (long long)jc * nr + ic];
+}
+
+template <int FAM>
+int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK;
+    const long long npix = (long long)sys->nrows * sys->ncols;
+    const long long fld = ((long long)sys->batch * sys->batch_stride + 3) & ~3ll;
+    int rc = pdegpu_scratch_reserve(ctx, (size_t)NUNK * fld * sizeof(float));
+    if (rc) return rc;
+    float *alt[2] = {(float *)ctx->scratch, (float *)ctx->scratch + fld};
+    bool al = (sys->nrows % 4 == 0) && (sys->batch_stride % 4 == 0);
+    auto a16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    for (int n = 0; n < 4; n++) al = al && a16(sys->w[n]);
+    for (int q = 0; q < NUNK; q++) al = al && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]);
+    if (NUNK == 2) al = al && a16(sys->m);
+    SysView v = make_view(sys);
+    dim3 grid((sys->nrows + PT_I - 1) / PT_I, (sys->ncols + PT_J - 1) / PT_J, sys->batch);
+    const int per = 2 * sys->nrows + 2 * sys->ncols;
+    dim3 bgrid((per + 127) / 128, sys->batch);
+    float *cur[2] = {sys->x[0], sys->x[1]}, *nxt[2] = {alt[0], alt[1]};
+    for (int it = 0; it < iter; it++) {
+        v.x[0] = cur[0]; v.x[1] = cur[1];
+        PDEGPU_PROF(ctx, "rb_tile_kernel", sweep_bytes<FAM>() * (double)npix * sys->batch);
+        rb_tile_kernel<FAM><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega, al ? 1 : 0);
+        PDEGPU_LAUNCH_CHECK(ctx, "rb_tile_kernel");
+        PDEGPU_PROF(ctx, "border_fill_kernel", 0);
+        border_fill_tile_kernel<NUNK><<<bgrid, 128, 0, ctx->stream>>>(nxt[0], nxt[1], sys->nrows, sys->ncols, sys->batch_stride);
+        PDEGPU_LAUNCH_CHECK(ctx, "border_fill_kernel");
+        for (int q = 0; q < 2; q++) { float *t = cur[q]; cur[q] = nxt[q]; nxt[q] = t; }
+    }
+    if (cur[0] != sys->x[0]) {            // odd number of sweeps: the result sits in the scratch copy
+        for (int q = 0; q < NUNK; q++)
+            PDEGPU_CUDA_OK(ctx, cudaMemcpy2DAsync(sys->x[q], (size_t)sys->batch_stride * sizeof(float), cur[q], (size_t)sys->batch_stride * sizeof(float),
+                                                  (size_t)npix * sizeof(float), sys->batch, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return PDEGPU_OK;
+}
+
+}  // namespace
 
 int relax_stream_point(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
-    (void)ctx; (void)sys; (void)iter; (void)omega;
-    return PDEGPU_ERR_UNSUPPORTED;
+    static const int use_tiles = getenv("PDEGPU_POINT_TILES") ? atoi(getenv("PDEGPU_POINT_TILES")) : 1;
+    if (!use_tiles || sys->nrows < 3 || sys->ncols < 3) return PDEGPU_ERR_UNSUPPORTED;
+    switch (sys->family) {
+    case PDEGPU_FLOW_ELIN4: return run_point_tiles<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN4:
+    case PDEGPU_FLOW_LLIN8: return run_point_tiles<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_DISP_LLIN4: return run_point_tiles<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE4:       return run_point_tiles<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    default: return PDEGPU_ERR_UNSUPPORTED;                    // PDE8: 4-colour ordering, generation 0
+    }
 }
