@@ -18,6 +18,15 @@
 #pragma once
 #include "pdegpu_internal.cuh"
 
+// 1/x to 1 ulp (MUFU.RCP). A relaxation step is a contraction towards the reference's fixed point, so a 1-ulp
+// reciprocal changes nothing that can be observed at convergence; an IEEE division costs ~10 instructions.
+__device__ __forceinline__ float sweep_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // point update (interior pixels only: all neighbours exist)
 // ---------------------------------------------------------------------------------------------
@@ -37,8 +46,8 @@ __device__ __forceinline__ void point_formula(const float (&w)[4], const float (
         const float nb = xn[0][W_E] * wE + xn[0][W_W] * wW + xn[0][W_S] * wS + xn[0][W_N] * wN;
         const float tr = D[0];
         float inv, bt;
-        if (!is_nan(tr)) { inv = 1.0f / tr; bt = C[0]; }
-        else             { inv = 1.0f / sw; bt = 0.0f; }
+        if (!is_nan(tr)) { inv = sweep_rcp(tr); bt = C[0]; }
+        else             { inv = sweep_rcp(sw); bt = 0.0f; }
         out[0] = (1.0f - omega) * xc[0] + omega * (bt + nb) * inv;
         return;
     }
@@ -58,12 +67,12 @@ __device__ __forceinline__ void point_formula(const float (&w)[4], const float (
         float inv, val;
         if (F::NUNK == 2) {
             // flow: divisor tests isnan(D), right-hand side tests isnan(C) (opticalflowSolvers.c:118-149)
-            inv = 1.0f / (is_nan(D[q]) ? sw : sw + D[q]);
+            inv = sweep_rcp(is_nan(D[q]) ? sw : sw + D[q]);
             val = is_nan(C[q]) ? nb[q] : (nb[q] + C[q] - M * xc[1 - q]);
         } else {
             // disparity: both test isnan(Cu) (disparitySolvers.c:96-112)
             const bool t = !is_nan(C[q]);
-            inv = 1.0f / (t ? (D[q] + sw) : sw);
+            inv = sweep_rcp(t ? (D[q] + sw) : sw);
             val = t ? (nb[q] + C[q]) : nb[q];
         }
         out[q] = (1.0f - omega) * xc[q] + omega * (val * inv);

@@ -19,34 +19,26 @@
 namespace {
 
 constexpr int PT_I = 128, PT_J = 8, PT_H = 2;                 // tile and halo
-constexpr int PS_I = PT_I + 2 * PT_H, PS_J = PT_J + 2 * PT_H; // shared-memory extent
-constexpr int PS_P = PS_I + 1;                                // pitch
+constexpr int PT_C0 = 4;                                      // shared-memory column of the tile's first pixel (16-B aligned)
+constexpr int PS_I = PT_I + 2 * PT_C0, PS_J = PT_J + 2 * PT_H; // shared-memory extent (columns PT_C0-2 .. PT_C0+PT_I+1 are used)
+
+__device__ __forceinline__ float f4c(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
 template <int FAM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega, int aligned)
 {
     using F = Fam<FAM>;
     constexpr int NUNK = F::NUNK;
     constexpr int NF = NUNK * (F::LATE ? 2 : 1);              // fields kept in shared memory: x[q], then x0[q]
-    __shared__ float sm[NF][PS_J][PS_P];
+    __shared__ __align__(16) float sm[NF][PS_J][PS_I];
     const int nr = s.nrows, nc = s.ncols;
     const int i0 = blockIdx.x * PT_I, j0 = blockIdx.y * PT_J;
     const long long base = (long long)blockIdx.z * s.bstride;
     const int tid = threadIdx.x;
     const float *fld[4] = {s.x[0] + base, NUNK == 2 ? s.x[1] + base : nullptr,
                            F::LATE ? s.x0[0] + base : nullptr, (F::LATE && NUNK == 2) ? s.x0[1] + base : nullptr};
-    // 1. unknowns + halo (indices clamped into the image: clamped copies are never used by an interior update)
-    for (int t = tid; t < PS_I * PS_J; t += 256) {
-        const int li = t % PS_I, lj = t / PS_I;
-        const int gi = min(max(i0 + li - PT_H, 0), nr - 1), gj = min(max(j0 + lj - PT_H, 0), nc - 1);
-        const long long p = (long long)gj * nr + gi;
-#pragma unroll
-        for (int q = 0; q < NUNK; q++) {
-            sm[q][lj][li] = fld[q][p];
-            if (F::LATE) sm[NUNK + q][lj][li] = fld[2 + (NUNK == 2 ? q : 0)][p];
-        }
-    }
+    auto field = [&](int f) -> const float * { return fld[f < NUNK ? f : 2 + (NUNK == 2 ? f - NUNK : 0)]; };
     // coefficients of this thread's 4 pixels
     const int ti = (tid & 31) * 4, tj = tid >> 5;
     const int gi0 = i0 + ti, gj = j0 + tj;
@@ -67,71 +59,139 @@ rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, floa
         for (int q = 0; q < NUNK; q++) { C4[q] = ldv(s.c[q]); D4[q] = ldv(s.d[q]); }
         if (NUNK == 2) M4 = ldv(s.m);
     }
+    // the red pixels of the 1-pixel ring around the tile (recomputed here): 138 of them, one per thread, coefficients
+    // loaded now so that their latency overlaps everything else. Frame coordinates (origin = tile - 1): a pixel is
+    // red when li + lj is even (i0 and j0 are even).
+    int rli = -1, rlj = 0;
+    if (tid < 65) { rli = 2 * tid; rlj = 0; }
+    else if (tid < 130) { rli = 2 * (tid - 65) + 1; rlj = PT_J + 1; }
+    else if (tid < 134) { rli = 0; rlj = 2 * (tid - 130) + 2; }
+    else if (tid < 138) { rli = PT_I + 1; rlj = 2 * (tid - 134) + 1; }
+    float rw[4], rC[2], rD[2], rM = 0.f;
+    bool ring_ok = false;
+    if (rli >= 0) {
+        const int gi = i0 + rli - 1, gjr = j0 + rlj - 1;
+        ring_ok = gi >= 1 && gi <= nr - 2 && gjr >= 1 && gjr <= nc - 2;
+        const long long p = base + (long long)min(max(gjr, 0), nc - 1) * nr + min(max(gi, 0), nr - 1);
+#pragma unroll
+        for (int n = 0; n < 4; n++) rw[n] = s.w[n][p];
+        rC[0] = s.c[0][p]; rD[0] = s.d[0][p];
+        rC[1] = NUNK == 2 ? s.c[NUNK - 1][p] : 0.f; rD[1] = NUNK == 2 ? s.d[NUNK - 1][p] : 0.f;
+        if (NUNK == 2) rM = s.m[p];
+    }
+    // 1. unknowns + halo (indices clamped into the image: clamped copies are never used by an interior update).
+    //    The 128 tile columns of a row are one aligned run: float4 in, float4 out; the 2+2 halo elements are scalar.
+    if (aligned && i0 + PT_I <= nr) {
+        for (int t = tid; t < (PT_I / 4) * PS_J; t += 256) {
+            const int v = t % (PT_I / 4), lj = t / (PT_I / 4);
+            const int gj = min(max(j0 + lj - PT_H, 0), nc - 1);
+            const long long p = (long long)gj * nr + i0 + 4 * v;
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                *reinterpret_cast<float4 *>(&sm[f][lj][PT_C0 + 4 * v]) = *reinterpret_cast<const float4 *>(field(f) + p);
+        }
+    } else {
+        for (int t = tid; t < PT_I * PS_J; t += 256) {
+            const int li = t % PT_I, lj = t / PT_I;
+            const int gi = min(i0 + li, nr - 1), gj = min(max(j0 + lj - PT_H, 0), nc - 1);
+            const long long p = (long long)gj * nr + gi;
+#pragma unroll
+            for (int f = 0; f < NF; f++) sm[f][lj][PT_C0 + li] = field(f)[p];
+        }
+    }
+    for (int t = tid; t < 2 * PT_H * PS_J; t += 256) {
+        const int h = t % (2 * PT_H), lj = t / (2 * PT_H);
+        const int c = h < PT_H ? PT_C0 - PT_H + h : PT_C0 + PT_I + h - PT_H;       // columns 2,3 and 132,133
+        const int gi = min(max(i0 + c - PT_C0, 0), nr - 1), gj = min(max(j0 + lj - PT_H, 0), nc - 1);
+        const long long p = (long long)gj * nr + gi;
+#pragma unroll
+        for (int f = 0; f < NF; f++) sm[f][lj][c] = field(f)[p];
+    }
     __syncthreads();
 
-    // update of the pixel at shared-memory position (li, lj) from given coefficients
-    auto update = [&](int li, int lj, const float (&w)[4], const float (&C)[2], const float (&D)[2], float M) {
+    // scalar update of the pixel at shared-memory position (c, lj) (ring pixels)
+    auto update = [&](int c, int lj, const float (&w)[4], const float (&C)[2], const float (&D)[2], float M) {
         float xn[2][4], xc[2], x0n[2][4], x0c[2], out[2];
 #pragma unroll
         for (int q = 0; q < NUNK; q++) {
-            xc[q] = sm[q][lj][li];
-            xn[q][W_W] = sm[q][lj - 1][li]; xn[q][W_E] = sm[q][lj + 1][li];
-            xn[q][W_N] = sm[q][lj][li - 1]; xn[q][W_S] = sm[q][lj][li + 1];
+            xc[q] = sm[q][lj][c];
+            xn[q][W_W] = sm[q][lj - 1][c]; xn[q][W_E] = sm[q][lj + 1][c];
+            xn[q][W_N] = sm[q][lj][c - 1]; xn[q][W_S] = sm[q][lj][c + 1];
             if (F::LATE) {
-                x0c[q] = sm[NUNK + q][lj][li];
-                x0n[q][W_W] = sm[NUNK + q][lj - 1][li]; x0n[q][W_E] = sm[NUNK + q][lj + 1][li];
-                x0n[q][W_N] = sm[NUNK + q][lj][li - 1]; x0n[q][W_S] = sm[NUNK + q][lj][li + 1];
+                x0c[q] = sm[NUNK + q][lj][c];
+                x0n[q][W_W] = sm[NUNK + q][lj - 1][c]; x0n[q][W_E] = sm[NUNK + q][lj + 1][c];
+                x0n[q][W_N] = sm[NUNK + q][lj][c - 1]; x0n[q][W_S] = sm[NUNK + q][lj][c + 1];
             }
         }
         point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, M, omega, out);
 #pragma unroll
-        for (int q = 0; q < NUNK; q++) sm[q][lj][li] = out[q];
+        for (int q = 0; q < NUNK; q++) sm[q][lj][c] = out[q];
     };
+    // half-sweep on this thread's 4 pixels: one float4 per row and field out of shared memory (conflict-free),
+    // the updated unknowns go back as one float4; xk[q] keeps the thread's current values
+    float4 xk[2];
     auto own = [&](int colour) {
+        const int lj = tj + PT_H, c = PT_C0 + ti;
+        float4 vc[NF], vw[NF], ve[NF];
+        float lf[NF], rt[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            vc[f] = *reinterpret_cast<const float4 *>(&sm[f][lj][c]);
+            vw[f] = *reinterpret_cast<const float4 *>(&sm[f][lj - 1][c]);
+            ve[f] = *reinterpret_cast<const float4 *>(&sm[f][lj + 1][c]);
+            lf[f] = sm[f][lj][c - 1]; rt[f] = sm[f][lj][c + 4];
+        }
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) xk[q] = vc[q];
         if (!row_ok || gj < 1 || gj > nc - 2) return;
-#define V4(v, k) ((k) == 0 ? (v).x : (k) == 1 ? (v).y : (k) == 2 ? (v).z : (v).w)
+        float res[2][4];
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) { res[q][0] = vc[q].x; res[q][1] = vc[q].y; res[q][2] = vc[q].z; res[q][3] = vc[q].w; }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int gi = gi0 + k;
             if (gi < 1 || gi > nr - 2 || ((gi + gj) & 1) != colour) continue;
-            const float w[4] = {V4(w4[0], k), V4(w4[1], k), V4(w4[2], k), V4(w4[3], k)};
-            const float C[2] = {V4(C4[0], k), NUNK == 2 ? V4(C4[NUNK - 1], k) : 0.f};
-            const float D[2] = {V4(D4[0], k), NUNK == 2 ? V4(D4[NUNK - 1], k) : 0.f};
-            update(ti + k + PT_H, tj + PT_H, w, C, D, NUNK == 2 ? V4(M4, k) : 0.f);
+            float xn[2][4], xc[2], x0n[2][4], x0c[2], out[2];
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) {
+                xc[q] = f4c(vc[q], k);
+                xn[q][W_W] = f4c(vw[q], k); xn[q][W_E] = f4c(ve[q], k);
+                xn[q][W_N] = k > 0 ? f4c(vc[q], k - 1) : lf[q];
+                xn[q][W_S] = k < 3 ? f4c(vc[q], k + 1) : rt[q];
+                if (F::LATE) {
+                    x0c[q] = f4c(vc[NUNK + q], k);
+                    x0n[q][W_W] = f4c(vw[NUNK + q], k); x0n[q][W_E] = f4c(ve[NUNK + q], k);
+                    x0n[q][W_N] = k > 0 ? f4c(vc[NUNK + q], k - 1) : lf[NUNK + q];
+                    x0n[q][W_S] = k < 3 ? f4c(vc[NUNK + q], k + 1) : rt[NUNK + q];
+                }
+            }
+            const float w[4] = {f4c(w4[0], k), f4c(w4[1], k), f4c(w4[2], k), f4c(w4[3], k)};
+            const float C[2] = {f4c(C4[0], k), NUNK == 2 ? f4c(C4[NUNK - 1], k) : 0.f};
+            const float D[2] = {f4c(D4[0], k), NUNK == 2 ? f4c(D4[NUNK - 1], k) : 0.f};
+            point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, NUNK == 2 ? f4c(M4, k) : 0.f, omega, out);
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) res[q][k] = out[q];
         }
-#undef V4
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            xk[q] = make_float4(res[q][0], res[q][1], res[q][2], res[q][3]);
+            *reinterpret_cast<float4 *>(&sm[q][lj][c]) = xk[q];
+        }
     };
     // 2. red: own pixels, then the red pixels of the 1-pixel ring around the tile
     own(0);
-    {
-        constexpr int RING = 2 * (PT_I + 2) + 2 * PT_J;
-        for (int t = tid; t < RING; t += 256) {
-            int li, lj;                                       // position in the (PT_I+2) x (PT_J+2) frame, origin = tile - 1
-            if (t < PT_I + 2) { li = t; lj = 0; }
-            else if (t < 2 * (PT_I + 2)) { li = t - (PT_I + 2); lj = PT_J + 1; }
-            else if (t < 2 * (PT_I + 2) + PT_J) { li = 0; lj = 1 + t - 2 * (PT_I + 2); }
-            else { li = PT_I + 1; lj = 1 + t - 2 * (PT_I + 2) - PT_J; }
-            const int gi = i0 + li - 1, gjr = j0 + lj - 1;
-            if (gi < 1 || gi > nr - 2 || gjr < 1 || gjr > nc - 2 || ((gi + gjr) & 1) != 0) continue;
-            const long long p = base + (long long)gjr * nr + gi;
-            const float w[4] = {s.w[0][p], s.w[1][p], s.w[2][p], s.w[3][p]};
-            const float C[2] = {s.c[0][p], NUNK == 2 ? s.c[NUNK - 1][p] : 0.f};
-            const float D[2] = {s.d[0][p], NUNK == 2 ? s.d[NUNK - 1][p] : 0.f};
-            update(li + PT_H - 1, lj + PT_H - 1, w, C, D, NUNK == 2 ? s.m[p] : 0.f);
-        }
-    }
+    if (ring_ok) update(rli + PT_C0 - 1, rlj + PT_H - 1, rw, rC, rD, rM);
     __syncthreads();
     // 3. black
     own(1);
-    // 4. own pixels -> X_out (each thread wrote its own pixels last: no barrier needed)
+    // 4. own pixels -> X_out straight from registers
     if (row_ok) {
         float *xo[2] = {xo0 + base, NUNK == 2 ? xo1 + base : nullptr};
         const long long p = (long long)gj * nr + gi0;
 #pragma unroll
         for (int q = 0; q < NUNK; q++) {
-            const float *r = &sm[q][tj + PT_H][ti + PT_H];
-            if (aligned && gi0 + 3 < nr) *reinterpret_cast<float4 *>(xo[q] + p) = make_float4(r[0], r[1], r[2], r[3]);
-            else for (int k = 0; k < 4 && gi0 + k < nr; k++) xo[q][p + k] = r[k];
+            if (aligned && gi0 + 3 < nr) *reinterpret_cast<float4 *>(xo[q] + p) = xk[q];
+            else for (int k = 0; k < 4 && gi0 + k < nr; k++) xo[q][p + k] = f4c(xk[q], k);
         }
     }
 }
