@@ -379,6 +379,17 @@ int pdegpu_dev_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0
 int pdegpu_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
         int nrows, int ncols, int channels, int batch, const pdegpu_flow_llin_params *params);
 
+/* Iout = TVdenoise8(I_in)   matlab/denoising/TVdenoise8.m (BASELINE configs[3]: 8-neighbour anisotropic TV denoising):
+ * two-level pyramid, outer_iter+1 lagged-diffusivity steps per level of ADdiffWeights -> TRACE/B -> PDEsolver8,
+ * bilinear up-sampling. I_in: nrows x ncols x nframes single (as runme.m:118,144 passes it). */
+typedef struct pdegpu_tvdenoise8_params {
+    double alpha, omega, scl_factor;      /* 500, 1.75, 0.75 (:36-44) */
+    int outer_iter, inner_iter, solver;   /* 20, 4, 2 */
+} pdegpu_tvdenoise8_params;
+void pdegpu_tvdenoise8_default_params(pdegpu_tvdenoise8_params *p);
+int pdegpu_dev_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes, const pdegpu_tvdenoise8_params *params);
+int pdegpu_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes, const pdegpu_tvdenoise8_params *params);
+
 #ifdef __cplusplus
 }
 #endif

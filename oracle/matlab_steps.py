@@ -313,15 +313,17 @@ def ad_diff_weights(D, quantile=0.5):
 
 
 def tv_terms(Iout, Iin, weights, alpha):
-    """TVdenoise8.m:83-85: PsiData, TRACE, B (double), and the alpha-scaled weights handed to PDEsolver8."""
-    Iout = np.asarray(Iout, dtype=np.float64)
-    Iin = np.asarray(Iin, dtype=np.float64)
-    psi = 1.0 / np.sqrt((Iout - Iin) ** 2 + np.finfo(np.float64).eps)
+    """TVdenoise8.m:83-85 for SINGLE images (runme.m:118,144 passes single): PsiData and B are computed in single,
+    TRACE = single PsiData + double alpha*(sum of weights) -> single; plus the single(alpha*w) handed to PDEsolver8."""
+    Iout = np.asarray(Iout, dtype=F32)
+    Iin = np.asarray(Iin, dtype=F32)
+    df = (Iout - Iin).astype(F32)
+    psi = (F32(1) / np.sqrt((df * df).astype(F32) + F32(np.finfo(np.float64).eps))).astype(F32)
     sw = sum(weights)
     if psi.ndim == 3:                      # ADdiffWeights repmat's its weights over the frames (:221-230)
         sw = sw[:, :, None]
-    tr = psi + alpha * sw
-    return tr.astype(F32), (psi * Iin).astype(F32), [np.asarray(alpha * w, dtype=F32) for w in weights]
+    tr = (psi + (alpha * sw).astype(F32)).astype(F32)
+    return tr, (psi * Iin).astype(F32), [np.asarray(alpha * w, dtype=F32) for w in weights]
 
 
 def disp_sym_terms(d, dU, Udt, Udx, b1, b2, alpha, beta, srDiff):

@@ -62,3 +62,27 @@ def flow_llin(I0, I1, backend, alpha=0.0420, omega=1.9, firstLoop=4, secondLoop=
             U = ms.imresize_bilinear((U * up).astype(F32), output_size=size)
             V = ms.imresize_bilinear((V * up).astype(F32), output_size=size)
     return U, V
+
+
+def tvdenoise8(I_in, backend, alpha=500.0, omega=1.75, outer_iter=20, inner_iter=4, solver=2, scl_factor=0.75):
+    """Iout = TVdenoise8(I_in), matlab/denoising/TVdenoise8.m:36-115, for a single image rows x cols (x frames)."""
+    I_in = np.asarray(I_in, dtype=F32)
+    shape = I_in.shape
+    I0 = I_in.reshape(shape[0], shape[1], -1)
+    G = ms.fspecial_gaussian(5, 1.25)
+    I1 = ms.imresize_bilinear(I0, scale=scl_factor)                    # :60  (from the unsmoothed image)
+    I0 = ms.imfilter(I0, G)                                            # :65
+    # :68-74: the size test is met at scl = 2; the smoothed coarsest level is assigned to `Itin`, i.e. dropped
+    Iin = [I0, I1]
+    Iout = Iin[1].copy()
+    for s in (1, 0):
+        for _ in range(outer_iter + 1):                                # :79  iter = 0:outer_iter
+            w = ms.ad_diff_weights(Iout)                               # :81
+            TRACE, B, aw = ms.tv_terms(Iout, Iin[s], w[:8], alpha)     # :83-85
+            fr = Iout.shape[2]
+            aw3 = [np.repeat(x[:, :, None], fr, axis=2) for x in aw]
+            Iout = backend.call("PDEsolver8", [Iout, TRACE, B] + aw3 + [F32(inner_iter), F32(omega), F32(solver)], 1)[0]   # :87-100
+            Iout = np.asarray(Iout, dtype=F32).reshape(Iin[s].shape)
+        if s > 0:
+            Iout = ms.imresize_bilinear(Iout, output_size=Iin[0].shape[:2])   # :112
+    return Iout.reshape(shape)

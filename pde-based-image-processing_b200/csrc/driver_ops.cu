@@ -584,7 +584,7 @@ struct AdArgs {
     const float *Iout, *Iin;  // for TRACE/B
     const double *mx, *my, *nrm;
     const SelState *st;
-    int nr, nc, frames;
+    int nr, nc, frames, wframes;
     double scale;
 };
 
@@ -613,16 +613,22 @@ ad_weights_kernel(const AdArgs a)
     tensor(i + 1, j, tyy, txx, txy);      w[6] = i == nr - 1 ? 0.0 : 0.5 * (cxx + txx);                           // S
     tensor(i + 1, j - 1, tyy, txx, txy);  w[7] = (i == nr - 1 || j == 0) ? 0.0 : -0.25 * (cxy + txy);             // SW
     const long long p = (long long)j * nr + i;
+    // ADdiffWeights repmat's its weights over the frames (:221-230): one copy per frame when wframes > 1
+    for (int f = 0; f < a.wframes; f++) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) a.w[k][p] = (float)(a.scale * w[k]);
+        for (int k = 0; k < 8; k++) a.w[k][(long long)f * nr * nc + p] = (float)(a.scale * w[k]);
+    }
     if (a.TRACE) {
+        // TVdenoise8.m:83-85 with single images (runme.m:118,144): PsiData and B in single, TRACE = single + double -> single
         const double sw = ((((((w[0] + w[1]) + w[2]) + w[3]) + w[4]) + w[5]) + w[6]) + w[7];
+        const float asw = (float)(a.scale * sw);
         for (int f = 0; f < a.frames; f++) {
             const long long q = (long long)f * nr * nc + p;
-            const double io = (double)a.Iout[q], ii = (double)a.Iin[q];
-            const double psi = 1.0 / sqrt((io - ii) * (io - ii) + 2.220446049250313e-16);
-            a.TRACE[q] = (float)(psi + a.scale * sw);
-            a.B[q] = (float)(psi * ii);
+            const float io = a.Iout[q], ii = a.Iin[q];
+            const float df = subf(io, ii);
+            const float psi = __fdiv_rn(1.0f, __fsqrt_rn(addf(mulf(df, df), 2.220446049250313e-16f)));
+            a.TRACE[q] = addf(psi, asw);
+            a.B[q] = mulf(psi, ii);
         }
     }
 }
@@ -630,7 +636,7 @@ ad_weights_kernel(const AdArgs a)
 }  // namespace
 
 int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin,
-                       int nr, int nc, int frames, double quantile, double scale, double *lambda_dev)
+                       int nr, int nc, int frames, double quantile, double scale, double *lambda_dev, int wframes)
 {
     const long long n = (long long)nr * nc;
     const size_t need = 3 * n * sizeof(double) + sizeof(SelState) + 256;
@@ -656,7 +662,7 @@ int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *
     for (int k = 0; k < 8; k++) a.w[k] = w[k];
     a.TRACE = TRACE; a.B = B; a.Iout = D; a.Iin = Iin;
     a.mx = mx; a.my = my; a.nrm = nrm; a.st = st;
-    a.nr = nr; a.nc = nc; a.frames = frames; a.scale = scale;
+    a.nr = nr; a.nc = nc; a.frames = frames; a.wframes = wframes < 1 ? 1 : wframes; a.scale = scale;
     PDEGPU_PROF(ctx, "ad_weights_kernel", (24.0 + 32.0 + (TRACE ? 16.0 * frames : 0.0)) * n);
     ad_weights_kernel<<<grid2(nr, nc, 1), 256, 0, ctx->stream>>>(a);
     PDEGPU_LAUNCH_CHECK(ctx, "ad_weights_kernel");

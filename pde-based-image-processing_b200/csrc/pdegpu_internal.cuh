@@ -141,4 +141,4 @@ int op_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, in
 int op_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n);
 int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V, int nr, int nc, int batch, long long stride);
 int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long n);
-int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin, int nr, int nc, int frames, double quantile, double scale, double *lambda_dev);
+int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin, int nr, int nc, int frames, double quantile, double scale, double *lambda_dev, int wframes = 1);

@@ -238,3 +238,98 @@ extern "C" int pdegpu_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const fl
     PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return PDEGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// TVdenoise8 (matlab/denoising/TVdenoise8.m, BASELINE configs[3] "8-neighbour anisotropic TV denoising"):
+// two-level pyramid (:59-75), per level outer_iter+1 lagged-diffusivity steps of
+// { ADdiffWeights (:81), PsiData/TRACE/B (:83-85), PDEsolver8 (:87-100) }, bilinear up-sampling (:112).
+// The driver's typo at :72 (`Itin{scl} = imfilter(...)`: the coarsest level is NOT smoothed) is kept.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int tv_run(pdegpu_ctx *ctx, Bump &b, float *Iout, const float *Iin, int nrows, int ncols, int F, const pdegpu_tvdenoise8_params &P)
+{
+    const bool dry = b.dry;
+    const int r1 = (int)ceil(nrows * P.scl_factor), c1 = (int)ceil(ncols * P.scl_factor);
+    const size_t n0 = (size_t)nrows * ncols, n1 = (size_t)r1 * c1;
+    float *in0 = b.take(n0 * F), *in1 = b.take(n1 * F), *X = b.take(n0 * F), *X2 = b.take(n0 * F), *tmp = b.take(n0 * F);
+    float *TR = b.take(n0 * F), *BB = b.take(n0 * F), *w[8];
+    for (int k = 0; k < 8; k++) w[k] = b.take(n0 * F);
+    if (dry) return PDEGPU_OK;
+    double G[25];
+    gaussian5(1.25, G);
+    // Iin{2} from the unsmoothed Iin{1}, then Iin{1} smoothed (:60-66); the size test of :68 is always met at scl = 2
+    RC(pdegpu_dev_imresize_bilinear(ctx, in1, tmp, Iin, nrows, ncols, r1, c1, P.scl_factor, P.scl_factor, 1, F));
+    RC(op_imfilter(ctx, in0, Iin, nrows, ncols, F, n0, n0, G, 5, 5, 1, 1.0f));
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(X, in1, n1 * F * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));     // Iout = Iin{scales}
+    for (int s = 1; s >= 0; s--) {
+        const int nr = s ? r1 : nrows, nc = s ? c1 : ncols;
+        const size_t n = (size_t)nr * nc;
+        const float *in = s ? in1 : in0;
+        for (int it = 0; it <= P.outer_iter; it++) {
+            RC(op_ad_diff_weights(ctx, w, TR, BB, X, in, nr, nc, F, 0.5, P.alpha, nullptr, F));
+            pdegpu_system sys;
+            memset(&sys, 0, sizeof sys);
+            sys.family = PDEGPU_PDE8; sys.nrows = nr; sys.ncols = nc; sys.batch = F; sys.batch_stride = n;
+            sys.x[0] = X; sys.c[0] = BB; sys.d[0] = TR;
+            // ADdiffWeights returns [W NW N NE E SE S SW]
+            sys.w[W_W] = w[0]; sys.w[W_NW] = w[1]; sys.w[W_N] = w[2]; sys.w[W_NE] = w[3];
+            sys.w[W_E] = w[4]; sys.w[W_SE] = w[5]; sys.w[W_S] = w[6]; sys.w[W_SW] = w[7];
+            RC(pdegpu_dev_relax(ctx, &sys, P.inner_iter, (float)P.omega, P.solver));
+        }
+        if (s > 0) {
+            RC(pdegpu_dev_imresize_bilinear(ctx, X2, tmp, X, nr, nc, nrows, ncols, (double)nrows / nr, (double)ncols / nc, 1, F));
+            PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(X, X2, n0 * F * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(Iout, X, n0 * F * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PDEGPU_OK;
+}
+
+}  // namespace
+
+extern "C" void pdegpu_tvdenoise8_default_params(pdegpu_tvdenoise8_params *p)
+{
+    p->alpha = 500; p->omega = 1.75; p->outer_iter = 20; p->inner_iter = 4; p->solver = 2; p->scl_factor = 0.75;   // TVdenoise8.m:36-44
+}
+
+extern "C" int pdegpu_dev_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes,
+        const pdegpu_tvdenoise8_params *params)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!Iout || !Iin || !params) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_tvdenoise8: null pointer");
+    if (nrows < 8 || ncols < 8 || nframes < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_dev_tvdenoise8: bad shape");
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    Bump b = {nullptr, 0, 0, true};
+    int rc = tv_run(ctx, b, Iout, Iin, nrows, ncols, nframes, *params);
+    if (rc) return rc;
+    if (b.used > ctx->work_bytes) {
+        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->work) cudaFree(ctx->work);
+        ctx->work = nullptr; ctx->work_bytes = 0;
+        if (cudaMalloc((void **)&ctx->work, b.used) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_tvdenoise8: cannot allocate %zu bytes of workspace", b.used); }
+        ctx->work_bytes = b.used;
+    }
+    Bump w = {ctx->work, ctx->work_bytes, 0, false};
+    return tv_run(ctx, w, Iout, Iin, nrows, ncols, nframes, *params);
+}
+
+extern "C" int pdegpu_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes,
+        const pdegpu_tvdenoise8_params *params)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!Iout || !Iin || !params) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_tvdenoise8: null pointer");
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t nb = (size_t)nrows * ncols * nframes * sizeof(float);
+    pdegpu_arena_reset(ctx);
+    int rc = pdegpu_arena_reserve(ctx, 2 * nb + 1024);
+    if (rc) return rc;
+    float *di = (float *)pdegpu_arena_alloc(ctx, nb), *dout = (float *)pdegpu_arena_alloc(ctx, nb);
+    if (!di || !dout) return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_tvdenoise8: arena exhausted");
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(di, Iin, nb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pdegpu_dev_tvdenoise8(ctx, dout, di, nrows, ncols, nframes, params);
+    if (rc) return rc;
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(Iout, dout, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PDEGPU_OK;
+}

@@ -60,6 +60,12 @@ class DispSymTerms(ctypes.Structure):
                 ("CuG", c_void_p), ("DuG", c_void_p)]
 
 
+class TvParams(ctypes.Structure):
+    """Mirror of `pdegpu_tvdenoise8_params`."""
+    _fields_ = [("alpha", ctypes.c_double), ("omega", ctypes.c_double), ("scl_factor", ctypes.c_double),
+                ("outer_iter", c_int), ("inner_iter", c_int), ("solver", c_int)]
+
+
 class FlowLlinParams(ctypes.Structure):
     """Mirror of `pdegpu_flow_llin_params`."""
     _fields_ = [("alpha", ctypes.c_double), ("omega", ctypes.c_double), ("b1", ctypes.c_double), ("b2", ctypes.c_double),
@@ -138,6 +144,11 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_dev_ad_diff_weights.restype = c_int
         L.pdegpu_dev_ad_diff_weights.argtypes = [c_void_p, POINTER(c_void_p * 8), c_void_p, c_void_p, c_void_p, c_void_p,
                                                  c_int, c_int, c_int, c_double, c_double, c_void_p]
+        L.pdegpu_tvdenoise8_default_params.restype = None
+        L.pdegpu_tvdenoise8_default_params.argtypes = [POINTER(TvParams)]
+        for fn in (L.pdegpu_dev_tvdenoise8, L.pdegpu_tvdenoise8):
+            fn.restype = c_int
+            fn.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(TvParams)]
         L.pdegpu_flow_llin_default_params.restype = None
         L.pdegpu_flow_llin_default_params.argtypes = [POINTER(FlowLlinParams)]
         for fn in (L.pdegpu_dev_flow_llin_2d, L.pdegpu_flow_llin_2d):
@@ -209,6 +220,21 @@ class Context:
 
     def lhs(self, sys: System, nframes: int, AU: int, AV: int):
         self._chk(dll().pdegpu_dev_lhs(self.h, ctypes.byref(sys), nframes, AU, AV))
+
+    def tvdenoise8(self, I, **overrides):
+        """Iout = TVdenoise8(I): I numpy [rows, cols(, frames)] single. Host-pointer entry point."""
+        import numpy as np
+        I = np.asarray(I, dtype=np.float32)
+        I3 = I.reshape(I.shape[0], I.shape[1], -1)
+        nr, nc, fr = I3.shape
+        p = TvParams()
+        dll().pdegpu_tvdenoise8_default_params(ctypes.byref(p))
+        for k, v in overrides.items():
+            setattr(p, k, v)
+        a = np.ascontiguousarray(I3.reshape(-1, order="F"))
+        out = np.empty_like(a)
+        self._chk(dll().pdegpu_tvdenoise8(self.h, out.ctypes.data, a.ctypes.data, nr, nc, fr, ctypes.byref(p)))
+        return out.reshape((nr, nc, fr), order="F").reshape(I.shape)
 
     def flow_llin(self, I0, I1, params: "FlowLlinParams | None" = None, **overrides):
         """[U V] = FlowEminND_llin_2D_v10 for one pair or a batch: I0, I1 numpy [rows, cols, channels] or
