@@ -335,6 +335,12 @@ int pdegpu_dev_imresize_bilinear(pdegpu_ctx *ctx, float *out, float *tmp, const 
         int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols,
         int antialias, int planes);
 
+/* Same with imresize's default 'bicubic' kernel (the FMG and Horn-Schunck drivers up-sample the flow with it:
+ * FlowEminNDFASFMG_elin_2D_v10.m:180-181, FlowEminHS_elin_2D_v10.m:189-190). */
+int pdegpu_dev_imresize_bicubic(pdegpu_ctx *ctx, float *out, float *tmp, const float *in,
+        int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols,
+        int antialias, int planes);
+
 /* out = medfilt2(in, [3 3], 'symmetric')  (FlowEminND_llin_2D_v10.m:354-355) */
 int pdegpu_dev_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes, long long stride);
 

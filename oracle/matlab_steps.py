@@ -84,19 +84,25 @@ def medfilt2_symmetric(A):
     return np.sort(np.stack(st, axis=-1), axis=-1)[..., 4]
 
 
-def imresize_contributions(in_len, out_len, scale, antialias=True):
+def imresize_contributions(in_len, out_len, scale, antialias=True, cubic=False):
     """indices (0-based) and weights of imresize's triangle ('bilinear') kernel along one dimension:
     output sample x (1-based) sits at u = x/scale + 0.5(1 - 1/scale); when shrinking with antialiasing the
     kernel is stretched by 1/scale; weights are normalised; out-of-range taps are mirrored."""
-    kw = 2.0
+    kw = 4.0 if cubic else 2.0
     if scale < 1 and antialias:
         kw = kw / scale
 
+    def base(x):
+        ax = np.abs(x)
+        if cubic:                            # imresize's cubic convolution kernel (a = -0.5)
+            ax2, ax3 = ax * ax, ax * ax * ax
+            return (1.5 * ax3 - 2.5 * ax2 + 1.0) * (ax <= 1) + (-0.5 * ax3 + 2.5 * ax2 - 4.0 * ax + 2.0) * ((1 < ax) & (ax <= 2))
+        return np.maximum(0.0, 1.0 - ax)
+
     def h(x):
         if scale < 1 and antialias:
-            x = x * scale
-            return scale * np.maximum(0.0, 1.0 - np.abs(x))
-        return np.maximum(0.0, 1.0 - np.abs(x))
+            return scale * base(x * scale)
+        return base(x)
 
     x = np.arange(1, out_len + 1, dtype=np.float64)
     u = x / scale + 0.5 * (1.0 - 1.0 / scale)
@@ -110,7 +116,12 @@ def imresize_contributions(in_len, out_len, scale, antialias=True):
     return ind - 1, w
 
 
-def imresize_bilinear(A, scale=None, output_size=None, antialias=True):
+def imresize_bicubic(A, scale=None, output_size=None, antialias=True):
+    """imresize(A, ...) with the default 'bicubic' method."""
+    return imresize_bilinear(A, scale, output_size, antialias, cubic=True)
+
+
+def imresize_bilinear(A, scale=None, output_size=None, antialias=True, cubic=False):
     """imresize(A, scale, 'bilinear') / imresize(A, 'OutputSize', [r c], 'Method', 'triangle'|'bilinear').
     The dimension with the smaller scale factor is resized first (rows first on a tie)."""
     A = np.asarray(A)
@@ -126,12 +137,12 @@ def imresize_bilinear(A, scale=None, output_size=None, antialias=True):
     order = [0, 1] if sr <= sc else [1, 0]
     for dim in order:                                        # each pass: double accumulation, result in the class of A
         if dim == 0:
-            ind, w = imresize_contributions(rows, orows, sr, antialias)
+            ind, w = imresize_contributions(rows, orows, sr, antialias, cubic)
             acc = np.zeros((orows,) + out.shape[1:], dtype=np.float64)
             for p in range(w.shape[1]):
                 acc += w[:, p].reshape((-1,) + (1,) * (out.ndim - 1)) * out[ind[:, p]].astype(np.float64)
         else:
-            ind, w = imresize_contributions(cols, ocols, sc, antialias)
+            ind, w = imresize_contributions(cols, ocols, sc, antialias, cubic)
             acc = np.zeros((out.shape[0], ocols) + out.shape[2:], dtype=np.float64)
             for p in range(w.shape[1]):
                 acc += w[:, p].reshape((1, -1) + (1,) * (out.ndim - 2)) * out[:, ind[:, p]].astype(np.float64)
@@ -353,3 +364,34 @@ def disp_sym_terms(d, dU, Udt, Udx, b1, b2, alpha, beta, srDiff):
                 acc = p[:, :, c].astype(F32).copy() if acc is None else (acc + p[:, :, c]).astype(F32)
         return acc
     return s3([gD * CuD, -gS * CuS]), s3([gD * DuD, gS * DuS])
+
+
+def fmg_derivatives(It0, It1):
+    """Derivative stacks of one level of the FMG driver, FlowEminNDFASFMG_elin_2D_v10.m:81-141 (single images 0..255).
+    Returns (Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy)."""
+    pre = np.array([[0.037659, 0.249724, 0.439911, 0.249724, 0.037659]])
+    odx = np.array([[0.104550, 0.292315, 0.0, -0.292315, -0.104550]])
+    odx_s = odx / 255
+    oxx = np.array([[0.232905, 0.002668, -0.471147, 0.002668, 0.232905]])
+    It0 = np.asarray(It0, dtype=F32); It1 = np.asarray(It1, dtype=F32)
+    f = lambda A, h: imfilter(A, h, "replicate", conv=True)
+    Ist = (((It0 + It1).astype(F32) * F32(0.55)).astype(F32) / F32(255)).astype(F32)
+    Idt = ((It0 - It1).astype(F32) / F32(255)).astype(F32)
+    Idx = f(f(Ist, pre.T), odx); Idy = f(f(Ist, pre), odx.T)
+    Idxx = f(f(Ist, pre.T), oxx); Idyy = f(f(Ist, pre), oxx.T)
+    Idxy = f(f(Ist, odx), odx.T)
+    Idxt = (f(f(It0, pre.T), odx_s) - f(f(It1, pre.T), odx_s)).astype(F32)
+    Idyt = (f(f(It0, pre), odx_s.T) - f(f(It1, pre), odx_s.T)).astype(F32)
+    return Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy
+
+
+def fmg_terms(der, b1, b2):
+    """M, Cu, Cv, Du, Dv of FlowEminNDFASFMG_elin_2D_v10.m:143-149 (single, evaluated left to right)."""
+    Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy = [np.asarray(x, dtype=F32) for x in der]
+    b1, b2 = F32(b1), F32(b2)
+    M = b1 * Idy * Idx + b2 * Idxy * (Idxx + Idyy)
+    Cu = b1 * Idt * Idx + b2 * (Idxt * Idxx + Idyt * Idxy)
+    Cv = b1 * Idt * Idy + b2 * (Idxt * Idxy + Idyt * Idyy)
+    Du = b1 * Idx * Idx + b2 * (Idxx * Idxx + Idxy * Idxy)
+    Dv = b1 * Idy * Idy + b2 * (Idxy * Idxy + Idyy * Idyy)
+    return M, Cu, Cv, Du, Dv

@@ -86,3 +86,77 @@ def tvdenoise8(I_in, backend, alpha=500.0, omega=1.75, outer_iter=20, inner_iter
         if s > 0:
             Iout = ms.imresize_bilinear(Iout, output_size=Iin[0].shape[:2])   # :112
     return Iout.reshape(shape)
+
+
+def flow_fmg(I0, I1, backend, alpha=0.035, omega=1.9, firstLoop=4, iter=4, b1=0.03, b2=0.97, scl_factor=0.5, solver=2,
+             cycle_index=1, max_scales=None):
+    """[U V] = FlowEminNDFASFMG_elin_2D_v10(cat(3, I0, I1), channels): full multigrid (FMG) over a lpf pyramid, one FAS
+    V-cycle (cycle_index = 1) or W-cycle (2) per level. I0, I1: rows x cols x channels, 0..255.
+    matlab/optical_flow/FlowEminNDFASFMG_elin_2D_v10.m, line numbers in the comments."""
+    I0 = np.asarray(I0, dtype=F32).reshape(I0.shape[0], I0.shape[1], -1)                               # :72
+    I1 = np.asarray(I1, dtype=F32).reshape(I1.shape[0], I1.shape[1], -1)
+    G = ms.fspecial_gaussian(5, 1.0)                                                                    # :97
+    It0, It1 = [ms.imfilter(I0, G, conv=True)], [ms.imfilter(I1, G, conv=True)]                         # :103-104
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :106-118
+        It0.append(ms.lpf_decimate(It0[-1])); It1.append(ms.lpf_decimate(It1[-1]))
+        if It0[-1].shape[0] <= 10 or It0[-1].shape[1] <= 10:
+            break
+    S = len(It0)
+    der = [ms.fmg_derivatives(It0[s], It1[s]) for s in range(S)]                                        # :123-141
+    coef = [ms.fmg_terms(der[s], b1, b2) for s in range(S)]                                             # :143-149
+    P = dict(alpha=alpha, omega=omega, firstLoop=firstLoop, iter=iter, b1=b1, b2=b2, scl_factor=scl_factor,
+             solver=solver, cycle_index=cycle_index)
+
+    def smooth(U, V, s, Cu, Cv, want_res):                                                              # :367-464
+        M, _, _, Du, Dv = coef[s]
+        for _ in range(P["firstLoop"]):
+            _, MG, CuG, CvG, DuG, DvG = ms.elin_terms(der[s], (M, Cu, Cv, Du, Dv), U, V, b1, b2, alpha, True)
+            wW, wN, wS, wE = [w.astype(F32) for w in ms.op_diff_weights(U, V)]
+            U, V = backend.call("Oflow_sor_elin4_2d", [U, V, MG, CuG, CvG, DuG, DvG, wW, wN, wE, wS,
+                                                       F32(P["iter"]), F32(omega), F32(solver)], 2)
+        if not want_res:
+            return U, V, None, None
+        _, MG, CuG, CvG, DuG, DvG = ms.elin_terms(der[s], (M, Cu, Cv, Du, Dv), U, V, b1, b2, alpha, False)
+        wW, wN, wS, wE = [w.astype(F32) for w in ms.op_diff_weights(U, V)]
+        out = backend.call("Oflow_sor_elin4_2d", [U, V, MG, CuG, CvG, DuG, DvG, wW, wN, wE, wS,
+                                                  F32(0), F32(omega), F32(solver)], 4)                # iter = 0: residuals only (:446-460)
+        ch = der[s][0].shape[2]
+        return U, V, out[2].reshape(U.shape + (ch,)), out[3].reshape(U.shape + (ch,))
+
+    def fas_cycle(U, V, Cu, Cv, s):                                                                     # :193-273
+        Uc = None
+        if s < S - 1:
+            for _ in range(P["cycle_index"]):
+                U, V, RU, RV = smooth(U, V, s, Cu, Cv, True)                                            # :207
+                RUr, RVr = ms.fw_restrict(RU, scl_factor), ms.fw_restrict(RV, scl_factor)               # :212-213
+                Ur, Vr = ms.fw_restrict(U, scl_factor), ms.fw_restrict(V, scl_factor)                   # :216-217
+                Mc, _, _, Duc, Dvc = coef[s + 1]
+                gd, MG, _, _, DuG, DvG = ms.elin_terms(der[s + 1], (Mc, Mc, Mc, Duc, Dvc), Ur, Vr, b1, b2, alpha, False)   # :225-237
+                wW, wN, wS, wE = [w.astype(F32) for w in ms.op_diff_weights(Ur, Vr)]                    # :234
+                Au, Av = backend.call("Oflow_lhs_elin4_2d", [Ur, Vr, MG, DuG, DvG, wW, wN, wE, wS], 2)  # :239-248
+                ch = gd.shape[2]
+                fu = ms.fas_rhs(RUr.reshape(gd.shape), Au.reshape(gd.shape), gd)                        # :250-251
+                fv = ms.fas_rhs(RVr.reshape(gd.shape), Av.reshape(gd.shape), gd)
+                Uc, Vc = fas_cycle(Ur, Vr, fu, fv, s + 1)                                               # :253
+                up = F32(1.0 / scl_factor)
+                U = (U + ms.imresize_bilinear(((Uc - Ur) * up).astype(F32), output_size=U.shape)).astype(F32)   # :256-257
+                V = (V + ms.imresize_bilinear(((Vc - Vr) * up).astype(F32), output_size=V.shape)).astype(F32)
+        else:
+            U, V, _, _ = smooth(U, V, s, Cu, Cv, False)                                                 # :261-263
+        if Uc is not None:
+            U, V, _, _ = smooth(U, V, s, Cu, Cv, False)                                                 # :269
+        return U, V
+
+    U = V = None
+    for s in range(S - 1, -1, -1):                                                                      # :158
+        rows, cols = It0[s].shape[:2]
+        if U is None:
+            U = np.zeros((rows, cols), F32); V = np.zeros((rows, cols), F32)
+        U, V = fas_cycle(U, V, coef[s][1], coef[s][2], s)                                               # :174
+        if s > 0:                                                                                       # :179-182
+            up = F32(1.0 / scl_factor)
+            size = It0[s - 1].shape[:2]
+            U = ms.imresize_bicubic((U * up).astype(F32), output_size=size)
+            V = ms.imresize_bicubic((V * up).astype(F32), output_size=size)
+    return U, V

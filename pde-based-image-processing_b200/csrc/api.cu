@@ -564,22 +564,45 @@ extern "C" int pdegpu_dev_imfilter(pdegpu_ctx *ctx, float *out, const float *in,
     return op_imfilter(ctx, out, in, nrows, ncols, planes, in_stride, out_stride, h, kr, kc, step, prescale);
 }
 
+int imresize_2d(pdegpu_ctx *ctx, float *out, float *tmp, const float *in, int in_rows, int in_cols, int out_rows, int out_cols,
+                double scale_rows, double scale_cols, int antialias, int planes, int cubic)
+{
+    // imresize resizes the dimension with the smaller scale factor first (rows on a tie)
+    int rc;
+    if (scale_rows <= scale_cols) {
+        rc = op_imresize_dim(ctx, tmp, in, 0, in_rows, out_rows, in_cols, scale_rows, antialias, planes, (long long)in_rows * in_cols, (long long)out_rows * in_cols, cubic);
+        if (rc) return rc;
+        return op_imresize_dim(ctx, out, tmp, 1, in_cols, out_cols, out_rows, scale_cols, antialias, planes, (long long)out_rows * in_cols, (long long)out_rows * out_cols, cubic);
+    }
+    rc = op_imresize_dim(ctx, tmp, in, 1, in_cols, out_cols, in_rows, scale_cols, antialias, planes, (long long)in_rows * in_cols, (long long)in_rows * out_cols, cubic);
+    if (rc) return rc;
+    return op_imresize_dim(ctx, out, tmp, 0, in_rows, out_rows, out_cols, scale_rows, antialias, planes, (long long)in_rows * out_cols, (long long)out_rows * out_cols, cubic);
+}
+
+static int imresize_check(pdegpu_ctx *ctx, const void *out, const void *tmp, const void *in, int in_rows, int in_cols, int out_rows, int out_cols,
+                          double scale_rows, double scale_cols, int planes)
+{
+    if (!out || !tmp || !in || in_rows < 1 || in_cols < 1 || out_rows < 1 || out_cols < 1 || planes < 1 || !(scale_rows > 0) || !(scale_cols > 0))
+        return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_imresize: bad argument");
+    return PDEGPU_OK;
+}
+
 extern "C" int pdegpu_dev_imresize_bilinear(pdegpu_ctx *ctx, float *out, float *tmp, const float *in,
         int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes)
 {
     PDEGPU_ENTER(ctx);
-    if (!out || !tmp || !in || in_rows < 1 || in_cols < 1 || out_rows < 1 || out_cols < 1 || planes < 1 || !(scale_rows > 0) || !(scale_cols > 0))
-        return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_imresize_bilinear: bad argument");
-    // imresize resizes the dimension with the smaller scale factor first (rows on a tie)
-    int rc;
-    if (scale_rows <= scale_cols) {
-        rc = op_imresize_dim(ctx, tmp, in, 0, in_rows, out_rows, in_cols, scale_rows, antialias, planes, (long long)in_rows * in_cols, (long long)out_rows * in_cols);
-        if (rc) return rc;
-        return op_imresize_dim(ctx, out, tmp, 1, in_cols, out_cols, out_rows, scale_cols, antialias, planes, (long long)out_rows * in_cols, (long long)out_rows * out_cols);
-    }
-    rc = op_imresize_dim(ctx, tmp, in, 1, in_cols, out_cols, in_rows, scale_cols, antialias, planes, (long long)in_rows * in_cols, (long long)in_rows * out_cols);
+    int rc = imresize_check(ctx, out, tmp, in, in_rows, in_cols, out_rows, out_cols, scale_rows, scale_cols, planes);
     if (rc) return rc;
-    return op_imresize_dim(ctx, out, tmp, 0, in_rows, out_rows, out_cols, scale_rows, antialias, planes, (long long)in_rows * out_cols, (long long)out_rows * out_cols);
+    return imresize_2d(ctx, out, tmp, in, in_rows, in_cols, out_rows, out_cols, scale_rows, scale_cols, antialias, planes, 0);
+}
+
+extern "C" int pdegpu_dev_imresize_bicubic(pdegpu_ctx *ctx, float *out, float *tmp, const float *in,
+        int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes)
+{
+    PDEGPU_ENTER(ctx);
+    int rc = imresize_check(ctx, out, tmp, in, in_rows, in_cols, out_rows, out_cols, scale_rows, scale_cols, planes);
+    if (rc) return rc;
+    return imresize_2d(ctx, out, tmp, in, in_rows, in_cols, out_rows, out_cols, scale_rows, scale_cols, antialias, planes, 1);
 }
 
 extern "C" int pdegpu_dev_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nrows, int ncols, int planes, long long stride)

@@ -257,6 +257,7 @@ struct ResizeArgs {
     int in_len, out_len, other;   // `other` = length of the untouched dimension
     double scale;
     int antialias;
+    int cubic;                // 0: triangle (bilinear), 1: Matlab's cubic convolution kernel (bicubic)
     long long istride, ostride;
 };
 
@@ -269,27 +270,28 @@ imresize_kernel(float *__restrict__ out, const float *__restrict__ in, const Res
     if (i >= onr) return;
     in += (long long)blockIdx.z * a.istride;
     const bool shrink = a.scale < 1.0 && a.antialias;
-    const double kw = shrink ? 2.0 / a.scale : 2.0;
+    const double kw0 = a.cubic ? 4.0 : 2.0;
+    const double kw = shrink ? kw0 / a.scale : kw0;
     const int x = (a.dim == 0 ? i : j) + 1;                   // 1-based output coordinate
     const double u = (double)x / a.scale + 0.5 * (1.0 - 1.0 / a.scale);
     const int left = (int)floor(u - kw / 2.0);
     const int P = (int)ceil(kw) + 2;
+    auto h = [&](double d) -> double {
+        if (shrink) d *= a.scale;
+        const double ax = fabs(d);
+        double f;
+        if (a.cubic) {
+            const double ax2 = ax * ax, ax3 = ax2 * ax;
+            f = (1.5 * ax3 - 2.5 * ax2 + 1.0) * (ax <= 1.0 ? 1.0 : 0.0)
+              + (-0.5 * ax3 + 2.5 * ax2 - 4.0 * ax + 2.0) * ((1.0 < ax && ax <= 2.0) ? 1.0 : 0.0);
+        } else f = fmax(0.0, 1.0 - ax);
+        return shrink ? a.scale * f : f;
+    };
     double wsum = 0.0, acc = 0.0;
+    for (int p = 0; p < P; p++) wsum += h(u - (double)(left + p));
     for (int p = 0; p < P; p++) {
         const int ind = left + p;                             // 1-based input coordinate
-        double d = u - (double)ind;
-        double w;
-        if (shrink) { d *= a.scale; w = a.scale * fmax(0.0, 1.0 - fabs(d)); }
-        else w = fmax(0.0, 1.0 - fabs(d));
-        wsum += w;
-    }
-    for (int p = 0; p < P; p++) {
-        const int ind = left + p;
-        double d = u - (double)ind;
-        double w;
-        if (shrink) { d *= a.scale; w = a.scale * fmax(0.0, 1.0 - fabs(d)); }
-        else w = fmax(0.0, 1.0 - fabs(d));
-        w /= wsum;
+        const double w = h(u - (double)ind) / wsum;
         const int src = mirrori(ind - 1, a.in_len);
         const float v = a.dim == 0 ? in[(long long)j * inr + src] : in[(long long)src * inr + i];
         acc += w * (double)v;
@@ -441,9 +443,10 @@ int op_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, in
 }
 
 int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int in_len, int out_len, int other, double scale,
-                    int antialias, int planes, long long istride, long long ostride)
+                    int antialias, int planes, long long istride, long long ostride, int cubic)
 {
     ResizeArgs a;
+    a.cubic = cubic;
     a.dim = dim; a.in_len = in_len; a.out_len = out_len; a.other = other; a.scale = scale; a.antialias = antialias;
     a.istride = istride; a.ostride = ostride;
     const int onr = dim == 0 ? out_len : other, onc = dim == 0 ? other : out_len;
@@ -667,5 +670,54 @@ int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *
     ad_weights_kernel<<<grid2(nr, nc, 1), 256, 0, ctx->stream>>>(a);
     PDEGPU_LAUNCH_CHECK(ctx, "ad_weights_kernel");
     if (lambda_dev) PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(lambda_dev, &st->lambda, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PDEGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constant terms of the FMG early-linearisation driver, FlowEminNDFASFMG_elin_2D_v10.m:143-149, per channel:
+//   M = b1*Idy.*Idx + b2*Idxy.*(Idxx+Idyy), Cu = b1*Idt.*Idx + b2*(Idxt.*Idxx + Idyt.*Idxy), ... (single, left to right)
+// and the pre-scaling of :124-125: Ist = (It0+It1).*0.55/255, Idt = (It0-It1)/255.
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+fmg_terms_kernel(float *__restrict__ M, float *__restrict__ Cu, float *__restrict__ Cv, float *__restrict__ Du, float *__restrict__ Dv,
+                 const float *__restrict__ Idt, const float *__restrict__ Idx, const float *__restrict__ Idy,
+                 const float *__restrict__ Idxt, const float *__restrict__ Idyt, const float *__restrict__ Idxx,
+                 const float *__restrict__ Idyy, const float *__restrict__ Idxy, float b1, float b2, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float dt = Idt[t], dx = Idx[t], dy = Idy[t], xt = Idxt[t], yt = Idyt[t], xx = Idxx[t], yy = Idyy[t], xy = Idxy[t];
+    M[t]  = addf(mulf(mulf(b1, dy), dx), mulf(mulf(b2, xy), addf(xx, yy)));
+    Cu[t] = addf(mulf(mulf(b1, dt), dx), mulf(b2, addf(mulf(xt, xx), mulf(yt, xy))));
+    Cv[t] = addf(mulf(mulf(b1, dt), dy), mulf(b2, addf(mulf(xt, xy), mulf(yt, yy))));
+    Du[t] = addf(mulf(mulf(b1, dx), dx), mulf(b2, addf(mulf(xx, xx), mulf(xy, xy))));
+    Dv[t] = addf(mulf(mulf(b1, dy), dy), mulf(b2, addf(mulf(xy, xy), mulf(yy, yy))));
+}
+
+__global__ void __launch_bounds__(256)
+fmg_prescale_kernel(float *__restrict__ Ist, float *__restrict__ Idt, const float *__restrict__ I0, const float *__restrict__ I1, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    Ist[t] = __fdiv_rn(mulf(addf(I0[t], I1[t]), 0.55f), 255.0f);
+    Idt[t] = __fdiv_rn(subf(I0[t], I1[t]), 255.0f);
+}
+}  // namespace
+
+int op_fmg_terms(pdegpu_ctx *ctx, float *const out[5], const float *const der[8], float b1, float b2, long long n)
+{
+    PDEGPU_PROF(ctx, "fmg_terms_kernel", 52.0 * n);
+    fmg_terms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out[0], out[1], out[2], out[3], out[4],
+        der[0], der[1], der[2], der[3], der[4], der[5], der[6], der[7], b1, b2, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "fmg_terms_kernel");
+    return PDEGPU_OK;
+}
+
+int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n)
+{
+    PDEGPU_PROF(ctx, "fmg_prescale_kernel", 16.0 * n);
+    fmg_prescale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(Ist, Idt, I0, I1, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "fmg_prescale_kernel");
     return PDEGPU_OK;
 }

@@ -136,9 +136,12 @@ int op_fas_rhs(pdegpu_ctx *ctx, float *f, const float *R, const float *A, const 
 int op_imfilter(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long istride, long long ostride,
                 const double *h, int kr, int kc, int step, float prescale);
 int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int in_len, int out_len, int other, double scale,
-                    int antialias, int planes, long long istride, long long ostride);
+                    int antialias, int planes, long long istride, long long ostride, int cubic = 0);
 int op_medfilt3(pdegpu_ctx *ctx, float *out, const float *in, int nr, int nc, int planes, long long stride);
 int op_axpby(pdegpu_ctx *ctx, float *out, float a, const float *x, float b, const float *y, long long n);
 int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const float *V, int nr, int nc, int batch, long long stride);
 int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long n);
 int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin, int nr, int nc, int frames, double quantile, double scale, double *lambda_dev, int wframes = 1);
+int op_fmg_terms(pdegpu_ctx *ctx, float *const out[5], const float *const der[8], float b1, float b2, long long n);
+int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n);
+int imresize_2d(pdegpu_ctx *ctx, float *out, float *tmp, const float *in, int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes, int cubic);
