@@ -385,6 +385,24 @@ int pdegpu_dev_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0
 int pdegpu_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
         int nrows, int ncols, int channels, int batch, const pdegpu_flow_llin_params *params);
 
+/* [U V] = FlowEminNDFASFMG_elin_2D_v10(cat(3, I0, I1), channels)   matlab/optical_flow/FlowEminNDFASFMG_elin_2D_v10.m
+ * (BASELINE configs[2]: early-linearisation flow with full multigrid): Gaussian + lpf pyramid (:97-118), derivative
+ * stacks and constant terms per level (:123-149), FMG coarse to fine with one FAS V-cycle (cycle_index 1) or W-cycle (2)
+ * per level (:158-273) around the smoother (:367-464), bicubic up-sampling of the flow between levels (:180-181).
+ * I0, I1: nrows x ncols x channels per pair, values 0..255 (the driver does not rescale, :72); pair b starts at
+ * b*nrows*ncols*channels; U, V: nrows x ncols per pair. Pairs of a batch run one after the other on the stream. */
+typedef struct pdegpu_flow_fmg_params {
+    double alpha, omega, b1, b2, scl_factor;   /* 0.035, 1.9, 0.03, 0.97, 0.5 (:53-59) */
+    int firstLoop, iter, solver;               /* 4, 4, 2 */
+    int cycle_index;                           /* 1 = V-cycle, 2 = W-cycle (:63-65) */
+    int max_scales;                            /* 0 = until a side is <= 10 pixels (:114) */
+} pdegpu_flow_fmg_params;
+void pdegpu_flow_fmg_default_params(pdegpu_flow_fmg_params *p);
+int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_fmg_params *params);
+int pdegpu_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_fmg_params *params);
+
 /* Iout = TVdenoise8(I_in)   matlab/denoising/TVdenoise8.m (BASELINE configs[3]: 8-neighbour anisotropic TV denoising):
  * two-level pyramid, outer_iter+1 lagged-diffusivity steps per level of ADdiffWeights -> TRACE/B -> PDEsolver8,
  * bilinear up-sampling. I_in: nrows x ncols x nframes single (as runme.m:118,144 passes it). */

@@ -24,9 +24,11 @@ constexpr int PS_I = PT_I + 2 * PT_C0, PS_J = PT_J + 2 * PT_H; // shared-memory 
 
 __device__ __forceinline__ float f4c(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
-template <int FAM>
+// ALIGNED is a compile-time flag: a run-time one makes ptxas predicate the vector and the scalar loads into one
+// instruction stream, where the (predicated-off) scalar loads wait for the vector loads that share their registers.
+template <int FAM, bool ALIGNED>
 __global__ void __launch_bounds__(256, 2)
-rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega, int aligned)
+rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega)
 {
     using F = Fam<FAM>;
     constexpr int NUNK = F::NUNK;
@@ -45,10 +47,11 @@ rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, floa
     float4 w4[4], C4[2], D4[2], M4;
     const bool row_ok = gj < nc && gi0 < nr;
     {
-        const long long p = base + (long long)min(gj, nc - 1) * nr + min(gi0, nr - 1);
-        const int room = nr - 1 - min(gi0, nr - 1);
+        const int gic = min(gi0, ALIGNED ? nr - 4 : nr - 1);     // (aligned: nr is a multiple of 4, the clamp keeps 16-B alignment)
+        const long long p = base + (long long)min(gj, nc - 1) * nr + gic;
+        const int room = nr - 1 - gic;
         auto ldv = [&](const float *f) -> float4 {
-            if (aligned && room >= 3) return *reinterpret_cast<const float4 *>(f + p);
+            if (ALIGNED) return *reinterpret_cast<const float4 *>(f + p);
             float4 v;
             v.x = f[p]; v.y = f[p + min(1, room)]; v.z = f[p + min(2, room)]; v.w = f[p + min(3, room)];
             return v;
@@ -81,7 +84,7 @@ rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, floa
     }
     // 1. unknowns + halo (indices clamped into the image: clamped copies are never used by an interior update).
     //    The 128 tile columns of a row are one aligned run: float4 in, float4 out; the 2+2 halo elements are scalar.
-    if (aligned && i0 + PT_I <= nr) {
+    if (ALIGNED && i0 + PT_I <= nr) {
         for (int t = tid; t < (PT_I / 4) * PS_J; t += 256) {
             const int v = t % (PT_I / 4), lj = t / (PT_I / 4);
             const int gj = min(max(j0 + lj - PT_H, 0), nc - 1);
@@ -190,7 +193,7 @@ rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, floa
         const long long p = (long long)gj * nr + gi0;
 #pragma unroll
         for (int q = 0; q < NUNK; q++) {
-            if (aligned && gi0 + 3 < nr) *reinterpret_cast<float4 *>(xo[q] + p) = xk[q];
+            if (ALIGNED) *reinterpret_cast<float4 *>(xo[q] + p) = xk[q];
             else for (int k = 0; k < 4 && gi0 + k < nr; k++) xo[q][p + k] = f4c(xk[q], k);
         }
     }
@@ -238,7 +241,8 @@ int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     for (int it = 0; it < iter; it++) {
         v.x[0] = cur[0]; v.x[1] = cur[1];
         PDEGPU_PROF(ctx, "rb_tile_kernel", sweep_bytes<FAM>() * (double)npix * sys->batch);
-        rb_tile_kernel<FAM><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega, al ? 1 : 0);
+        if (al) rb_tile_kernel<FAM, true><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega);
+        else rb_tile_kernel<FAM, false><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega);
         PDEGPU_LAUNCH_CHECK(ctx, "rb_tile_kernel");
         PDEGPU_PROF(ctx, "border_fill_kernel", 0);
         border_fill_tile_kernel<NUNK><<<bgrid, 128, 0, ctx->stream>>>(nxt[0], nxt[1], sys->nrows, sys->ncols, sys->batch_stride);

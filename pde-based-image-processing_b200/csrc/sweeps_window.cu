@@ -92,7 +92,7 @@ alr_window_kernel(const WinParams p)
     WinTask cur, nxt;
     int q = warp;
     while (q < Q && !decode(q, cur)) q += nwarps;
-    if (q < Q) { int e0, ec; first_element(0, e0, ec); raw[0].issue(s, cur, ec, n, al); }
+    if (q < Q) { int e0, ec; first_element(0, e0, ec); if (al) raw[0].template issue<true>(s, cur, ec, n); else raw[0].template issue<false>(s, cur, ec, n); }
 
     while (q < Q) {
         int q2 = q + nwarps;
@@ -114,8 +114,8 @@ alr_window_kernel(const WinParams p)
         for (int t = 0; t < NT; t++) {
             {
                 int e0n, ecn;
-                if (t + 1 < NT) { first_element(t + 1, e0n, ecn); if (e0n < LS) raw[(t + 1) & 1].issue(s, cur, ecn, n, al); }
-                else if (q2 < Q) { first_element(0, e0n, ecn); raw[0].issue(s, nxt, ecn, n, al); }
+                if (t + 1 < NT) { first_element(t + 1, e0n, ecn); if (e0n < LS) { if (al) raw[(t + 1) & 1].template issue<true>(s, cur, ecn, n); else raw[(t + 1) & 1].template issue<false>(s, cur, ecn, n); } }
+                else if (q2 < Q) { first_element(0, e0n, ecn); if (al) raw[0].template issue<true>(s, nxt, ecn, n); else raw[0].template issue<false>(s, nxt, ecn, n); }
             }
             int e0, ec;
             first_element(t, e0, ec);

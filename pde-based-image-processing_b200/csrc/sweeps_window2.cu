@@ -21,7 +21,21 @@ namespace {
 
 constexpr int kW2Threads = 384;
 
-template <int FAM, int DIR, int M>
+// Phase probes (build with -DW2_PROBE; never in the shipped library): cycles per warp role, summed over all warps.
+#ifdef W2_PROBE
+__device__ unsigned long long g_w2_probe[16];
+#define PROBE_DECL unsigned long long pr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt_ = clock64(); const long long pt0_ = pt_
+#define PROBE(k) do { const long long n_ = clock64(); pr_[k] += (unsigned long long)(n_ - pt_); pt_ = n_; } while (0)
+#define PROBE_FLUSH(base) do { if (lane == 0) { pr_[7] = (unsigned long long)(clock64() - pt0_); for (int k_ = 0; k_ < 8; k_++) atomicAdd(&g_w2_probe[(base) + k_], pr_[k_]); } } while (0)
+#define PROBE_USE(v) do { if (__float_as_uint(v) == 0x7fc12345u) __trap(); } while (0)
+#else
+#define PROBE_DECL
+#define PROBE(k)
+#define PROBE_FLUSH(base)
+#define PROBE_USE(v)
+#endif
+
+template <int FAM, int DIR, int M, bool AL>
 __global__ void __launch_bounds__(kW2Threads, 1)
 alr_window2_kernel(const WinParams p)
 {
@@ -33,7 +47,12 @@ alr_window2_kernel(const WinParams p)
     constexpr int LS = 32 * M;
     constexpr int P = LS;
     constexpr int SP = NUNK * P + 4;
-    constexpr int NT = (LS + 127) / 128;
+    // pixels per lane and batch, batches in flight per lane. Measured (B200, 64 x 480x640, us per pass, lines of 480 / 640):
+    // VW 4 single-buffered 395 / 448, VW 2 double-buffered 411 / 542 (same bytes in flight per lane -- the register file
+    // is the limit -- and twice the load instructions).
+    constexpr int VW = 4;
+    constexpr bool DOUBLE = VW == 2;
+    constexpr int NT = (LS + 32 * VW - 1) / (32 * VW);
     constexpr int BUF = RF::N * LS;                           // floats per row buffer
     extern __shared__ float smem[];
     const int R = p.R, D = p.D, NBR = R >> 3, NA = p.NA, NS = p.NS, NBUF = p.NBUF;
@@ -54,8 +73,7 @@ alr_window2_kernel(const WinParams p)
     const int Ltot = 8 * nblk + (redundant ? 1 : 0);
     const int Q = D + 2 * ((Ltot + 1) >> 1);
     const float omega = p.omega, om1 = 1.0f - p.omega;
-    const int ec_last = (n - 1) & ~3;
-    const bool al = p.aligned != 0;
+    const int ec_last = (n - 1) & ~(VW - 1);
 
     auto decode = [&](int q, WinTask &T) -> bool {
         if (q < D) { T.l = 2 * q; T.odd = false; }
@@ -77,12 +95,28 @@ alr_window2_kernel(const WinParams p)
 
     if (warp < NA) {
         // =============================== assembler warps ===============================
-        for (int q = warp; q < Q; q += NA) {
+        // A lane owns VW consecutive pixels of a batch (batch t = elements 32*VW*t ..). Two batches are in flight:
+        // the loads of batch t+1 (or of the first batch of this warp's next line) are issued before batch t is
+        // touched, so a line costs one exposed memory latency instead of one per batch.
+        PROBE_DECL;
+        RawBatch<FAM, VW> rawA, rawB;
+        WinTask T, Tn;
+        int q = warp;
+        bool valid = q < Q && decode(q, T);
+        auto first_el = [&](int t, int &e0, int &ec) { e0 = 32 * VW * t + VW * lane; ec = min(e0, ec_last); };
+        auto issue_to = [&](RawBatch<FAM, VW> &rb, const WinTask &TT, int t) {
+            int e0, ec;
+            first_el(t, e0, ec);
+            if (e0 < LS) rb.template issue<AL>(s, TT, ec, n);
+        };
+        if (valid) issue_to(rawA, T, 0);
+        for (; q < Q; q += NA) {
             const int bi = q % NBUF;
             const unsigned use = (unsigned)(q / NBUF);
-            WinTask T;
-            const bool valid = decode(q, T);
+            const bool validn = q + NA < Q && decode(q + NA, Tn);
+            PROBE(0);
             warp_wait_ge(&freed_seq[bi], use, lane);          // the buffer's previous rows have been picked up
+            PROBE(1);
             if (valid) {
                 const int l = T.l;
                 if (l >= R) {                                 // ring slot free (see sweeps_window.cu)
@@ -90,61 +124,104 @@ alr_window2_kernel(const WinParams p)
                     warp_wait_ge(&written_seq[lbp % NBR], (unsigned)lbp + 1, lane);
                     if (lbp > 0) warp_wait_ge(&written_seq[(lbp - 1) % NBR], (unsigned)lbp, lane);
                 }
+                PROBE(2);
                 float *buf = bufs + (size_t)bi * BUF;
                 float *rs = ring + (size_t)(l % R) * SP;
                 const float *rsW = ring + (size_t)((l + R - 1) % R) * SP, *rsE = ring + (size_t)((l + 1) % R) * SP;
-#pragma unroll 1
-                for (int t = 0; t < NT; t++) {
-                    const int e0 = 128 * t + 4 * lane;
-                    const int ec = min(e0, ec_last);
-                    RawBatch<FAM> rb;
-                    if (e0 < LS) rb.issue(s, T, ec, n, al);
-                    if (t == 0 && T.odd) {
-                        warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
-                        if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
-                    }
-                    if (e0 < LS) {
-                        if (T.odd) rb.neighbours_from_ring(rsW, rsE, P, ec, n);
-                        float ra[4], rc[4], rb1[4], rd1[4], rb2[4], rd2[4], rm[4], xo0[4], xo1[4];
+                auto rows_of = [&](RawBatch<FAM, VW> &rb, int t) {
+                    int e0, ec;
+                    first_el(t, e0, ec);
+                    if (e0 >= LS) return;
+                    if (T.odd) rb.neighbours_from_ring(rsW, rsE, P, ec, n);
+                    float ra[VW], rc[VW], rb1[VW], rd1[VW], rb2[VW], rd2[VW], rm[VW], xo0[VW], xo1[VW];
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            PixelRaw<FAM, DIR> r;
-                            const bool ok = e0 + k < n;
-                            rb.template pixel<DIR>(k, ec + k, n, T.eW, T.eE, r);
-                            float a, c, b[2], d[2], m;
-                            r.rows(a, c, b, d, m);
-                            ra[k] = ok ? a : 0.f; rc[k] = ok ? c : 0.f;
-                            rb1[k] = ok ? b[qa] : 1.0f; rd1[k] = ok ? d[qa] : 0.f;
-                            rb2[k] = ok ? b[qb] : 1.0f; rd2[k] = ok ? d[qb] : 0.f;
-                            rm[k] = ok ? m : 0.f;
-                            xo0[k] = ok ? r.xo[0] : 0.f; xo1[k] = (ok && NUNK == 2) ? r.xo[NUNK - 1] : 0.f;
+                    for (int k = 0; k < VW; k++) {
+                        PixelRaw<FAM, DIR> r;
+                        const bool ok = e0 + k < n;
+                        rb.template pixel<DIR>(k, ec + k, n, T.eW, T.eE, r);
+                        float a, c, b[2], d[2], m;
+                        r.rows(a, c, b, d, m);
+                        ra[k] = ok ? a : 0.f; rc[k] = ok ? c : 0.f;
+                        rb1[k] = ok ? b[qa] : 1.0f; rd1[k] = ok ? d[qa] : 0.f;
+                        rb2[k] = ok ? b[qb] : 1.0f; rd2[k] = ok ? d[qb] : 0.f;
+                        rm[k] = ok ? m : 0.f;
+                        xo0[k] = ok ? r.xo[0] : 0.f; xo1[k] = (ok && NUNK == 2) ? r.xo[NUNK - 1] : 0.f;
+                    }
+                    stv(buf + RF::A * LS + e0, ra);
+                    stv(buf + RF::C * LS + e0, rc);
+                    stv(buf + RF::B1 * LS + e0, rb1);
+                    stv(buf + RF::D1 * LS + e0, rd1);
+                    stv(rs + e0, xo0);
+                    if (NUNK == 2) {
+                        stv(buf + RF::B2 * LS + e0, rb2);
+                        stv(buf + RF::D2 * LS + e0, rd2);
+                        stv(buf + RF::MM * LS + e0, rm);
+                        stv(rs + P + e0, xo1);
+                    }
+                };
+                if (DOUBLE) {
+#pragma unroll 1
+                    for (int t = 0; t < NT; t += 2) {
+                        PROBE(0);
+                        if (t + 1 < NT) issue_to(rawB, T, t + 1);
+                        PROBE(3);
+                        if (t == 0 && T.odd) {
+                            warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
+                            if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
                         }
-                        st4(buf + RF::A * LS + e0, ra);
-                        st4(buf + RF::C * LS + e0, rc);
-                        st4(buf + RF::B1 * LS + e0, rb1);
-                        st4(buf + RF::D1 * LS + e0, rd1);
-                        st4(rs + e0, xo0);
-                        if (NUNK == 2) {
-                            st4(buf + RF::B2 * LS + e0, rb2);
-                            st4(buf + RF::D2 * LS + e0, rd2);
-                            st4(buf + RF::MM * LS + e0, rm);
-                            st4(rs + P + e0, xo1);
+                        PROBE(4);
+                        PROBE_USE(rawA.w4[0].v[0]); PROBE_USE(rawA.XO4[0].v[0]);
+                        PROBE(5);
+                        rows_of(rawA, t);
+                        PROBE(6);
+                        // next user of rawA: batch t+2 of this line, or the first batch of this warp's next line
+                        if (t + 2 < NT) issue_to(rawA, T, t + 2);
+                        else if (validn) issue_to(rawA, Tn, 0);
+                        PROBE(3);
+                        if (t + 1 < NT) {
+                            PROBE_USE(rawB.w4[0].v[0]); PROBE_USE(rawB.XO4[0].v[0]);
+                            PROBE(5);
+                            rows_of(rawB, t + 1);
+                            PROBE(6);
                         }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int t = 0; t < NT; t++) {
+                        PROBE(0);
+                        if (t == 0 && T.odd) {
+                            warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
+                            if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
+                        }
+                        PROBE(4);
+                        PROBE_USE(rawA.w4[0].v[0]); PROBE_USE(rawA.XO4[0].v[0]);
+                        PROBE(5);
+                        rows_of(rawA, t);
+                        PROBE(6);
+                        // the batch is consumed: its registers take the next one (of this line, or of this warp's next line)
+                        if (t + 1 < NT) issue_to(rawA, T, t + 1);
+                        else if (validn) issue_to(rawA, Tn, 0);
+                        PROBE(3);
                     }
                 }
-            }
+            } else if (validn) issue_to(rawA, Tn, 0);
             __syncwarp();
             if (lane == 0) st_release(&filled_seq[bi], use + 1);
             __syncwarp();
+            T = Tn; valid = validn;
         }
+        PROBE_FLUSH(0);
     } else {
         // ================================= solver warps =================================
+        PROBE_DECL;
         for (int q = warp - NA; q < Q; q += NS) {
             const int bi = q % NBUF;
             const unsigned use = (unsigned)(q / NBUF);
             WinTask T;
             const bool valid = decode(q, T);
+            PROBE(0);
             warp_wait_ge(&filled_seq[bi], use + 1, lane);
+            PROBE(1);
             if (!valid) {
                 if (lane == 0) st_release(&freed_seq[bi], use + 1);
                 __syncwarp();
@@ -184,6 +261,7 @@ alr_window2_kernel(const WinParams p)
                 }
             }
             __syncwarp();
+            PROBE(2);
             unsigned done = 0;
             if (lane == 0) {
                 st_release(&solved_seq[l % R], (unsigned)l + 1);
@@ -221,24 +299,26 @@ alr_window2_kernel(const WinParams p)
                     st_release(&written_seq[lb % NBR], (unsigned)lb + 1);
                 }
                 __syncwarp();
+                PROBE(3);
             }
         }
+        PROBE_FLUSH(8);
     }
 }
 
-template <int FAM, int DIR, int M>
+template <int FAM, int DIR, int M, bool AL>
 int launch_window2(pdegpu_ctx *ctx, const WinParams &p, size_t smem, int batch)
 {
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window2_kernel)");
         attr_set[ctx->device & 15] = true;
     }
     const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_window2_kernel<dir0>" : "alr_window2_kernel<dir1,transposed>",
                 sweep_bytes<FAM>() * (double)p.n * p.nlines * batch);
-    alr_window2_kernel<FAM, DIR, M><<<grid, (p.NA + p.NS) * 32, smem, ctx->stream>>>(p);
+    alr_window2_kernel<FAM, DIR, M, AL><<<grid, (p.NA + p.NS) * 32, smem, ctx->stream>>>(p);
     PDEGPU_LAUNCH_CHECK(ctx, "alr_window2_kernel");
     return PDEGPU_OK;
 }
@@ -249,22 +329,29 @@ int window2_dispatch(pdegpu_ctx *ctx, WinParams &p, int M, int nunk, int batch)
     // geometry: 8 assemblers + 4 solvers; the ring as large as leaves room for >= 4 row buffers
     const int LS = 32 * M, SP = nunk * LS + 4, rowf = nunk == 2 ? 7 : 4;
     const size_t room = 227 * 1024;
-    p.NA = 8; p.NS = 4;
-    static const int RD[][2] = {{32, 5}, {24, 4}, {16, 3}};
+    static const int envNA = getenv("PDEGPU_W2_NA") ? atoi(getenv("PDEGPU_W2_NA")) : 8;       // tuning overrides (NA + NS <= 12)
+    static const int envNS = getenv("PDEGPU_W2_NS") ? atoi(getenv("PDEGPU_W2_NS")) : 4;
+    p.NA = envNA; p.NS = envNS;
+    if (p.NA < 1 || p.NS < 1 || p.NA + p.NS > kW2Threads / 32) return PDEGPU_ERR_UNSUPPORTED;
+    static const int envR = getenv("PDEGPU_W2_R") ? atoi(getenv("PDEGPU_W2_R")) : 0;          // ring lines (multiple of 8) / even lead
+    static const int envD = getenv("PDEGPU_W2_D") ? atoi(getenv("PDEGPU_W2_D")) : 0;
+    static const int envNBUF = getenv("PDEGPU_W2_NBUF") ? atoi(getenv("PDEGPU_W2_NBUF")) : 8;
+    const int RD[][2] = {{envR ? envR : 32, envD ? envD : 5}, {24, 4}, {16, 3}};
     for (auto &rd : RD) {
         const size_t fixed = ((size_t)rd[0] * SP + rd[0] + 2 * (rd[0] / 8) + 32) * sizeof(float);
         if (fixed >= room) continue;
         int nbuf = (int)((room - fixed) / ((size_t)rowf * LS * sizeof(float)));
-        if (nbuf > 8) nbuf = 8;
+        if (nbuf > envNBUF) nbuf = envNBUF;
+        if (nbuf > 16) nbuf = 16;
         if (nbuf < 4) continue;
         p.R = rd[0]; p.D = rd[1]; p.NBUF = nbuf;
         const size_t smem = fixed + (size_t)nbuf * rowf * LS * sizeof(float);
         switch (M) {
-        case 5:  return launch_window2<FAM, DIR, 5>(ctx, p, smem, batch);
-        case 9:  return launch_window2<FAM, DIR, 9>(ctx, p, smem, batch);
-        case 15: return launch_window2<FAM, DIR, 15>(ctx, p, smem, batch);
-        case 21: return launch_window2<FAM, DIR, 21>(ctx, p, smem, batch);
-        case 25: return launch_window2<FAM, DIR, 25>(ctx, p, smem, batch);
+        case 5: return p.aligned ? launch_window2<FAM, DIR, 5, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 5, false>(ctx, p, smem, batch);
+        case 9: return p.aligned ? launch_window2<FAM, DIR, 9, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 9, false>(ctx, p, smem, batch);
+        case 15: return p.aligned ? launch_window2<FAM, DIR, 15, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 15, false>(ctx, p, smem, batch);
+        case 21: return p.aligned ? launch_window2<FAM, DIR, 21, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 21, false>(ctx, p, smem, batch);
+        case 25: return p.aligned ? launch_window2<FAM, DIR, 25, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 25, false>(ctx, p, smem, batch);
         default: return PDEGPU_ERR_UNSUPPORTED;
         }
     }
@@ -272,6 +359,16 @@ int window2_dispatch(pdegpu_ctx *ctx, WinParams &p, int M, int nunk, int batch)
 }
 
 }  // namespace
+
+#ifdef W2_PROBE
+extern "C" int pdegpu_debug_w2_probe(unsigned long long *out16)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, g_w2_probe, sizeof(g_w2_probe)) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(g_w2_probe, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 // entry used by sweeps_window.cu: p is complete except for the geometry
 int window2_pass(pdegpu_ctx *ctx, int family, int dir, void *params, int M, int batch)

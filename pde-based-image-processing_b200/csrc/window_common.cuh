@@ -114,16 +114,32 @@ template <> struct RowF<1> { enum { A = 0, C = 1, B1 = 2, D1 = 3, B2 = 2, D2 = 3
 constexpr int kWinMaxWarps = 8;
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
-// 4 consecutive elements starting at p; unaligned lines: 4 scalar loads, clamped to the `room` elements left in the line
-__device__ __forceinline__ float4 ldv(const float *p, bool aligned, int room)
-{
-    if (aligned) return ld4(p);
-    float4 v;
-    v.x = p[0]; v.y = p[min(1, room)]; v.z = p[min(2, room)]; v.w = p[min(3, room)];
-    return v;
-}
 __device__ __forceinline__ void st4(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
-#define V4(v, kk) ((kk) == 0 ? (v).x : (kk) == 1 ? (v).y : (kk) == 2 ? (v).z : (v).w)
+__device__ __forceinline__ void stv(float *p, const float (&v)[4]) { st4(p, v); }
+__device__ __forceinline__ void stv(float *p, const float (&v)[2]) { *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]); }
+
+// VW consecutive elements starting at p, as ONE vector load (VW = 4: 16 B, VW = 2: 8 B). Unaligned lines: VW scalar
+// loads, clamped to the `room` elements left in the line.
+// (ALIGNED is a compile-time flag on purpose: with a run-time flag ptxas predicates both paths into one instruction
+// stream, and a predicated-off scalar load that names a register of an in-flight vector load still waits for it --
+// measured: one full memory latency in the middle of the load-issue block, profiles/r01_alr_window2_sass_regions.txt)
+template <int VW> struct Vec { float v[VW]; };
+template <int VW, bool ALIGNED>
+__device__ __forceinline__ Vec<VW> ldv(const float *p, int room)
+{
+    Vec<VW> r;
+    if (ALIGNED) {
+        if (VW == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); r.v[0] = t.x; r.v[1] = t.y; r.v[VW - 2] = t.z; r.v[VW - 1] = t.w; }
+        else         { const float2 t = *reinterpret_cast<const float2 *>(p); r.v[0] = t.x; r.v[VW - 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < VW; k++) r.v[k] = p[min(k, room)];
+    }
+    return r;
+}
+// same from shared memory (always aligned)
+template <int VW>
+__device__ __forceinline__ Vec<VW> ldsv(const float *p) { return ldv<VW, true>(p, VW); }
 
 // one line of a CTA's schedule
 struct WinTask {
@@ -131,33 +147,35 @@ struct WinTask {
     bool odd, eW, eE, owned;
 };
 
-// Raw operands of 4 consecutive pixels of a line (one float4 per field), loaded with no use of the values,
+// Raw operands of VW consecutive pixels of a line (one vector per field), loaded with no use of the values,
 // so that a lane can have the loads of two batches in flight.
-template <int FAM>
+template <int FAM, int VW = 4>
 struct RawBatch {
     using F = Fam<FAM>;
+    using V = Vec<VW>;
     static constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, NL = F::LATE ? F::NUNK : 1;
-    float4 w4[NN], C4[NUNK], D4[NUNK], XO4[NUNK], XW4[NUNK], XE4[NUNK], M4;
-    float4 X0C4[NL], X0W4[NL], X0E4[NL];
+    V w4[NN], C4[NUNK], D4[NUNK], XO4[NUNK], XW4[NUNK], XE4[NUNK], M4;
+    V X0C4[NL], X0W4[NL], X0E4[NL];
     float x0l[NUNK], x0r[NUNK];                                    // in-line neighbours beyond the vector
     float xWl[NUNK], xWr[NUNK], xEl[NUNK], xEr[NUNK];              // 8-neighbour: diagonal neighbours beyond the vector
     float x0Wl[NUNK], x0Wr[NUNK], x0El[NUNK], x0Er[NUNK];
 
     // ec = first element (clamped into the line), T = the line
-    __device__ __forceinline__ void issue(const SysView &s, const WinTask &T, int ec, int n, bool al)
+    template <bool AL>
+    __device__ __forceinline__ void issue(const SysView &s, const WinTask &T, int ec, int n)
     {
         const int ip = T.ibase + ec;
         const int room = n - 1 - ec;                          // elements after ec that are still inside the line
-#define ld4(ptr) ldv((ptr), al, room)
-        const int ipl = T.ibase + max(ec - 1, 0), ipr = T.ibase + min(ec + 4, n - 1);
+#define LDV(ptr) ldv<VW, AL>((ptr), room)
+        const int ipl = T.ibase + max(ec - 1, 0), ipr = T.ibase + min(ec + VW, n - 1);
         const int dW = T.dW, dE = T.dE;
 #pragma unroll
-        for (int nn = 0; nn < NN; nn++) w4[nn] = ld4(s.w[nn] + ip);
+        for (int nn = 0; nn < NN; nn++) w4[nn] = LDV(s.w[nn] + ip);
 #pragma unroll
         for (int qq = 0; qq < NUNK; qq++) {
-            C4[qq] = ld4(s.c[qq] + ip); D4[qq] = ld4(s.d[qq] + ip); XO4[qq] = ld4(s.x[qq] + ip);
+            C4[qq] = LDV(s.c[qq] + ip); D4[qq] = LDV(s.d[qq] + ip); XO4[qq] = LDV(s.x[qq] + ip);
             if (F::LATE) {
-                X0C4[qq] = ld4(s.x0[qq] + ip); X0W4[qq] = ld4(s.x0[qq] + ip + dW); X0E4[qq] = ld4(s.x0[qq] + ip + dE);
+                X0C4[qq] = LDV(s.x0[qq] + ip); X0W4[qq] = LDV(s.x0[qq] + ip + dW); X0E4[qq] = LDV(s.x0[qq] + ip + dE);
                 x0l[qq] = s.x0[qq][ipl]; x0r[qq] = s.x0[qq][ipr];
                 if (F::EIGHT) {
                     x0Wl[qq] = s.x0[qq][ipl + dW]; x0Wr[qq] = s.x0[qq][ipr + dW];
@@ -165,15 +183,15 @@ struct RawBatch {
                 }
             }
             if (!T.odd) {
-                XW4[qq] = ld4(s.x[qq] + ip + dW); XE4[qq] = ld4(s.x[qq] + ip + dE);
+                XW4[qq] = LDV(s.x[qq] + ip + dW); XE4[qq] = LDV(s.x[qq] + ip + dE);
                 if (F::EIGHT) {
                     xWl[qq] = s.x[qq][ipl + dW]; xWr[qq] = s.x[qq][ipr + dW];
                     xEl[qq] = s.x[qq][ipl + dE]; xEr[qq] = s.x[qq][ipr + dE];
                 }
             }
         }
-        if (NUNK == 2) M4 = ld4(s.m + ip);
-#undef ld4
+        if (NUNK == 2) M4 = LDV(s.m + ip);
+#undef LDV
     }
 
     // odd lines: the unknowns at the (even) neighbour lines come from the ring of solved lines
@@ -181,51 +199,49 @@ struct RawBatch {
     {
 #pragma unroll
         for (int qq = 0; qq < NUNK; qq++) {
-            XW4[qq] = ld4(rsW + qq * P + ec); XE4[qq] = ld4(rsE + qq * P + ec);
+            XW4[qq] = ldsv<VW>(rsW + qq * P + ec); XE4[qq] = ldsv<VW>(rsE + qq * P + ec);
             if (F::EIGHT) {
-                xWl[qq] = rsW[qq * P + max(ec - 1, 0)]; xWr[qq] = rsW[qq * P + min(ec + 4, n - 1)];
-                xEl[qq] = rsE[qq * P + max(ec - 1, 0)]; xEr[qq] = rsE[qq * P + min(ec + 4, n - 1)];
+                xWl[qq] = rsW[qq * P + max(ec - 1, 0)]; xWr[qq] = rsW[qq * P + min(ec + VW, n - 1)];
+                xEl[qq] = rsE[qq * P + max(ec - 1, 0)]; xEr[qq] = rsE[qq * P + min(ec + VW, n - 1)];
             }
         }
     }
 
-    // operands of pixel k (0..3) of the vector, in the form the row formulas take
+    // operands of pixel k (0..VW-1) of the vector, in the form the row formulas take
     template <int DIR>
     __device__ __forceinline__ void pixel(int k, int i, int n, bool eW, bool eE, PixelRaw<FAM, DIR> &r) const
     {
         const bool eN = i > 0, eS = i < n - 1;
+        const int km = k > 0 ? k - 1 : 0, kp = k < VW - 1 ? k + 1 : VW - 1;
         r.exmask = (eW ? 1u << W_W : 0u) | (eN ? 1u << W_N : 0u) | (eE ? 1u << W_E : 0u) | (eS ? 1u << W_S : 0u)
                  | (eN && eW ? 1u << W_NW : 0u) | (eN && eE ? 1u << W_NE : 0u) | (eS && eE ? 1u << W_SE : 0u) | (eS && eW ? 1u << W_SW : 0u);
 #pragma unroll
-        for (int nn = 0; nn < NN; nn++) r.w[nn] = V4(w4[nn], k);
+        for (int nn = 0; nn < NN; nn++) r.w[nn] = w4[nn].v[k];
 #pragma unroll
         for (int qq = 0; qq < NUNK; qq++) {
-            r.C[qq] = V4(C4[qq], k); r.D[qq] = V4(D4[qq], k); r.xo[qq] = V4(XO4[qq], k);
-            r.xn[qq][W_W] = V4(XW4[qq], k); r.xn[qq][W_E] = V4(XE4[qq], k);
+            r.C[qq] = C4[qq].v[k]; r.D[qq] = D4[qq].v[k]; r.xo[qq] = XO4[qq].v[k];
+            r.xn[qq][W_W] = XW4[qq].v[k]; r.xn[qq][W_E] = XE4[qq].v[k];
             if (F::EIGHT) {
-                r.xn[qq][W_NW % NN] = k > 0 ? V4(XW4[qq], k - 1) : xWl[qq];
-                r.xn[qq][W_SW % NN] = k < 3 ? V4(XW4[qq], k + 1) : xWr[qq];
-                r.xn[qq][W_NE % NN] = k > 0 ? V4(XE4[qq], k - 1) : xEl[qq];
-                r.xn[qq][W_SE % NN] = k < 3 ? V4(XE4[qq], k + 1) : xEr[qq];
+                r.xn[qq][W_NW % NN] = k > 0 ? XW4[qq].v[km] : xWl[qq];
+                r.xn[qq][W_SW % NN] = k < VW - 1 ? XW4[qq].v[kp] : xWr[qq];
+                r.xn[qq][W_NE % NN] = k > 0 ? XE4[qq].v[km] : xEl[qq];
+                r.xn[qq][W_SE % NN] = k < VW - 1 ? XE4[qq].v[kp] : xEr[qq];
             }
             if (F::LATE) {
-                r.x0c[qq] = V4(X0C4[qq], k);
-                r.x0n[qq][W_W] = V4(X0W4[qq], k); r.x0n[qq][W_E] = V4(X0E4[qq], k);
-                r.x0n[qq][W_N] = k > 0 ? V4(X0C4[qq], k - 1) : x0l[qq];
-                r.x0n[qq][W_S] = k < 3 ? V4(X0C4[qq], k + 1) : x0r[qq];
+                r.x0c[qq] = X0C4[qq].v[k];
+                r.x0n[qq][W_W] = X0W4[qq].v[k]; r.x0n[qq][W_E] = X0E4[qq].v[k];
+                r.x0n[qq][W_N] = k > 0 ? X0C4[qq].v[km] : x0l[qq];
+                r.x0n[qq][W_S] = k < VW - 1 ? X0C4[qq].v[kp] : x0r[qq];
                 if (F::EIGHT) {
-                    r.x0n[qq][W_NW % NN] = k > 0 ? V4(X0W4[qq], k - 1) : x0Wl[qq];
-                    r.x0n[qq][W_SW % NN] = k < 3 ? V4(X0W4[qq], k + 1) : x0Wr[qq];
-                    r.x0n[qq][W_NE % NN] = k > 0 ? V4(X0E4[qq], k - 1) : x0El[qq];
-                    r.x0n[qq][W_SE % NN] = k < 3 ? V4(X0E4[qq], k + 1) : x0Er[qq];
+                    r.x0n[qq][W_NW % NN] = k > 0 ? X0W4[qq].v[km] : x0Wl[qq];
+                    r.x0n[qq][W_SW % NN] = k < VW - 1 ? X0W4[qq].v[kp] : x0Wr[qq];
+                    r.x0n[qq][W_NE % NN] = k > 0 ? X0E4[qq].v[km] : x0El[qq];
+                    r.x0n[qq][W_SE % NN] = k < VW - 1 ? X0E4[qq].v[kp] : x0Er[qq];
                 }
             }
         }
-        r.M = NUNK == 2 ? V4(M4, k) : 0.f;
+        r.M = NUNK == 2 ? M4.v[k] : 0.f;
     }
 };
-
-
-#undef V4
 
 }  // namespace

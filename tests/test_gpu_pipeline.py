@@ -97,3 +97,55 @@ def test_tvdenoise8_default_parameters_quality(ctx):
     assert np.isfinite(g).all()
     assert abs(rm(g) - rm(o)) < 0.03 * rm(o), f"RMSE vs clean: GPU {rm(g)}, reference {rm(o)}, noisy {rm(noisy)}"
     assert float(np.mean(np.abs(g - o))) < 2e-2, f"mean |GPU - reference| = {float(np.mean(np.abs(g - o)))}"
+
+
+# ---- FlowEminNDFASFMG_elin_2D_v10 (BASELINE configs[2]): early linearisation + full multigrid ----
+def small_pair(seed, nr, nc, C):
+    """early linearisation = small displacements (the driver's own note): sub-pixel synthetic flow"""
+    I0, I1, u, v = synth.image_pair(seed, nr, nc, nframes=C, scale=255.0, max_flow=0.8)
+    return I0.reshape(nr, nc, C), I1.reshape(nr, nc, C), u, v
+
+
+@pytest.mark.parametrize("C,cycle", [(1, 1), (3, 1), (1, 2)])
+def test_fmg_converged_solves_match_reference(ctx, C, cycle):
+    """Every smoother call solved to convergence (iter = 600, omega = 1.6; the reference side is then within 5e-6 px of
+    its own limit): zebra (GPU) and lexicographic (reference)
+    line relaxation reach the same fixed point, so the whole FMG/FAS pipeline must agree to <= 1e-3 px mean EPE.
+    Four levels: with the 6x8 fifth level the reference's FAS iteration is itself unstable at converged inner solves
+    (the restatement on the reference MEX code diverges there too), which is not a property of the sweep."""
+    nr, nc = 96, 128
+    I0, I1, _, _ = small_pair(3, nr, nc, C)
+    kw = dict(iter=600, omega=1.6, firstLoop=2, max_scales=4 if cycle == 1 else 3, cycle_index=cycle)
+    Ug, Vg = ctx.flow_fmg(I0, I1, **kw)
+    Uo, Vo = pipelines.flow_fmg(I0, I1, backend(), **kw)
+    assert np.isfinite(Ug).all() and np.isfinite(Vg).all()
+    e = epe(Ug, Vg, Uo, Vo, margin=0)
+    assert e < 1e-3, f"mean EPE between GPU and reference FMG pipelines {e}"
+
+
+def test_fmg_driver_iteration_counts(ctx):
+    """At the driver's defaults (iter = 4, omega = 1.9) the two orderings are far from converged and differ: the
+    reference's lexicographic line sweeps carry information across the whole image in one sweep, zebra sweeps only
+    between neighbouring lines, so after 4 iterations the zebra iterate is the less accurate one (measured: AEE 0.10
+    against 0.03 px on this pair). Checked here: the default call is sane, and a moderate number
+    of sweeps (iter = 64 on four levels, ~0.1 s at 480x640) already agrees with the reference run the same way."""
+    nr, nc = 120, 160
+    I0, I1, u, v = small_pair(5, nr, nc, 1)
+    Ug, Vg = ctx.flow_fmg(I0, I1)
+    mag = float(np.mean(np.sqrt(u ** 2 + v ** 2)))
+    assert np.isfinite(Ug).all() and epe(Ug, Vg, u, v) < 0.6 * mag
+    kw = dict(iter=64, omega=1.6, max_scales=4)
+    Ug, Vg = ctx.flow_fmg(I0, I1, **kw)
+    Uo, Vo = pipelines.flow_fmg(I0, I1, backend(), **kw)
+    assert epe(Ug, Vg, Uo, Vo, margin=0) < 5e-3
+    assert abs(epe(Ug, Vg, u, v) - epe(Uo, Vo, u, v)) < 5e-3
+
+
+def test_fmg_batch_equals_single(ctx):
+    nr, nc = 64, 80
+    ps = [small_pair(20 + k, nr, nc, 1) for k in range(2)]
+    I0 = np.stack([p[0] for p in ps]); I1 = np.stack([p[1] for p in ps])
+    Ub, Vb = ctx.flow_fmg(I0, I1)
+    for k in range(2):
+        U1, V1 = ctx.flow_fmg(ps[k][0], ps[k][1])
+        assert np.array_equal(U1, Ub[k]) and np.array_equal(V1, Vb[k])

@@ -1,0 +1,43 @@
+"""CPU checks of the driver restatements in oracle/pipelines.py (they are the checker of tests/test_gpu_pipeline.py):
+run around the compiled reference MEX code (or the C restatement when oracle/_ref is absent) they must recover a known
+synthetic flow. Small sizes: the whole file runs in seconds."""
+import numpy as np
+
+from oracle import pipelines
+from pdegpu import synth
+
+
+def backend():
+    from oracle import oracle as o
+    return o.RefBackend() if o.have_ref() else o.OracleBackend()
+
+
+def aee(U, V, u, v, m=8):
+    s = (slice(m, U.shape[0] - m), slice(m, U.shape[1] - m))
+    return float(np.mean(np.sqrt((U[s] - u[s]) ** 2 + (V[s] - v[s]) ** 2)))
+
+
+def test_fmg_restatement_recovers_subpixel_flow():
+    nr, nc = 96, 128
+    I0, I1, u, v = synth.image_pair(3, nr, nc, nframes=1, scale=255.0, max_flow=0.8)
+    U, V = pipelines.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1), backend())
+    assert U.dtype == np.float32 and U.shape == (nr, nc) and np.isfinite(U).all()
+    e, mag = aee(U, V, u, v), float(np.mean(np.sqrt(u ** 2 + v ** 2)))
+    assert e < 0.05 and e < 0.25 * mag, f"AEE {e} for a mean displacement of {mag}"
+
+
+def test_fmg_pyramid_stops_at_ten_pixels():
+    # FlowEminNDFASFMG_elin_2D_v10.m:113-117: the level that reaches <= 10 pixels is the last one
+    nr, nc = 96, 128
+    I0, I1, _, _ = synth.image_pair(4, nr, nc, nframes=1, scale=255.0, max_flow=0.5)
+    a = pipelines.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1), backend())
+    b = pipelines.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1), backend(), max_scales=5)    # 96 48 24 12 6
+    c = pipelines.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1), backend(), max_scales=9)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], c[0])
+
+
+def test_llin_restatement_recovers_flow():
+    nr, nc = 64, 80
+    I0, I1, u, v = synth.image_pair(7, nr, nc, nframes=3, scale=255.0, max_flow=2.0)
+    U, V = pipelines.flow_llin(I0.reshape(nr, nc, 3), I1.reshape(nr, nc, 3), backend())
+    assert aee(U, V, u, v) < 0.25
