@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--band-iters", type=int, default=8, help="red-black sweeps per step")
     ap.add_argument("--band-T", type=int, default=1, help="sweeps per halo exchange (halo = 2T columns)")
     ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
+    ap.add_argument("--fmg-pairs", type=int, default=2, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -273,6 +274,91 @@ def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
 
 
 # ---------------------------------------------------------------------------------------------
+# FMG leg: BASELINE configs[2], the whole FlowEminNDFASFMG_elin_2D_v10 driver (early linearisation, full multigrid,
+# one FAS V-cycle per level, firstLoop=4, ALR iter=4) on synthetic 1920x1080 pairs, device resident and end to end
+# ---------------------------------------------------------------------------------------------
+def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
+    import torch
+    from pdegpu import lib, synth
+    NR, NC, C = 1080, 1920, 1                      # runme.m:90 runs this driver on single-channel frames
+    L = lib.dll()
+    p = lib.FlowFmgParams()
+    L.pdegpu_flow_fmg_default_params(ctypes.byref(p))
+    pair = synth.image_pair(300 + 7 * rank, NR, NC, nframes=C, scale=255.0, max_flow=0.8)
+    h0 = np.stack([pair[0].reshape(-1, order="F") for _ in range(FB)])
+    h1 = np.stack([pair[1].reshape(-1, order="F") for _ in range(FB)])
+    d0, d1 = torch.from_numpy(h0).to(dev), torch.from_numpy(h1).to(dev)
+    U = torch.empty(FB, NR * NC, device=dev)
+    V = torch.empty(FB, NR * NC, device=dev)
+    p0, p1 = torch.from_numpy(h0).pin_memory(), torch.from_numpy(h1).pin_memory()
+    Uh, Vh = torch.empty(FB, NR * NC).pin_memory(), torch.empty(FB, NR * NC).pin_memory()
+
+    def dev_run(pp):
+        ctx._chk(L.pdegpu_dev_flow_fmg_2d(ctx.h, U.data_ptr(), V.data_ptr(), d0.data_ptr(), d1.data_ptr(), NR, NC, C, FB, ctypes.byref(pp)))
+
+    def host_run():
+        ctx._chk(L.pdegpu_flow_fmg_2d(ctx.h, Uh.data_ptr(), Vh.data_ptr(), p0.data_ptr(), p1.data_ptr(), NR, NC, C, FB, ctypes.byref(p)))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    u, v = pair[2], pair[3]
+    sl = (slice(8, -8), slice(8, -8))
+
+    def aee_of(Ua, Va):
+        return float(np.mean(np.sqrt((Ua[sl] - u[sl]) ** 2 + (Va[sl] - v[sl]) ** 2)))
+
+    def timed(pp):
+        dev_run(pp)
+        barrier()
+        l0 = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(reps):
+            dev_run(pp)
+        ev1.record(stream)
+        barrier()
+        ms = maxr(ev0.elapsed_time(ev1)) / reps
+        Ug = U[0].cpu().numpy().reshape(NR, NC, order="F"); Vg = V[0].cpu().numpy().reshape(NR, NC, order="F")
+        return ms, (ctx.launches - l0) // reps, aee_of(Ug, Vg)
+
+    ms, launches, aee = timed(p)
+    host_run()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        host_run()
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0) / reps
+    out = {"metric": "1920x1080 flows/s (FlowEminNDFASFMG_elin_2D_v10 defaults: FMG, FAS V-cycle per level, firstLoop=4, ALR iter=4, 1 channel)",
+           "value": world * FB / (ms / 1e3), "unit": "flows/s", "pairs_per_gpu": FB, "ms_per_pair": ms / FB,
+           "gpu_launches_per_pair": int(launches // FB), "aee_vs_ground_truth_px": aee,
+           "e2e": {"value": world * FB / e2e_s, "unit": "flows/s", "h2d_bytes_per_step": int(2 * h0.nbytes),
+                   "d2h_bytes_per_step": int(2 * FB * NR * NC * 4), "api": "pdegpu_flow_fmg_2d (host pointers, pinned)"}}
+    if rank == 0 and world == 1:
+        from oracle import oracle as orc, pipelines
+        be = orc.RefBackend() if orc.have_ref() else orc.OracleBackend()
+        t0 = time.perf_counter()
+        Uo, Vo = pipelines.flow_fmg(pair[0].reshape(NR, NC, C), pair[1].reshape(NR, NC, C), be)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "flows/s", "cores": 1, "kind": "reference" if orc.have_ref() else "port",
+                               "sample": f"1 pair through oracle/pipelines.py (numpy restatement of the .m driver around the "
+                                         f"{be.name} MEX code), {dt:.1f} s",
+                               "aee_vs_ground_truth_px": aee_of(Uo, Vo)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # band workload: one very large image, column bands, halo exchange per T sweeps (strong scaling)
 # ---------------------------------------------------------------------------------------------
 def run_band(args):
@@ -473,6 +559,7 @@ def run_ours(args):
     assert os.environ.get("PDEGPU_DBG") or np.isfinite(out0.numpy()).all()
 
     flows = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_batch) if args.flow_batch > 0 else None
+    fmg = fmg_leg(ctx, dev, stream, dist, world, rank, args.fmg_pairs) if args.fmg_pairs > 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -504,6 +591,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": roof,
             "flows": flows,
+            "fmg": fmg,
             "kernels": prof,
             "clocks": clocks,
         }

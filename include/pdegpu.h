@@ -403,6 +403,22 @@ int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0,
 int pdegpu_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
         int nrows, int ncols, int channels, int batch, const pdegpu_flow_fmg_params *params);
 
+/* [U V] = FlowEminHS_elin_2D_v10(cat(3, I0, I1), channels)   matlab/optical_flow/FlowEminHS_elin_2D_v10.m
+ * (BASELINE configs[0]: Horn-Schunck): bilinear x scl_factor pyramid with 5x5 Gaussian smoothing (:96-115), per level
+ * derivative stacks and quadratic terms summed over channels (:139-172), ONE Oflow_sor_elin4_2d solve with constant
+ * weights alpha*channels (:127,174-188), 3x3 median + bicubic up-sampling of the flow (:193-196).
+ * Same array conventions as pdegpu_flow_fmg_2d; values 0..255 (the driver divides by 255, :66). */
+typedef struct pdegpu_flow_hs_params {
+    double alpha, omega, b1, b2, scl_factor;   /* 0.2, 1.9, 0.25, 0.75, 0.75 (:48-53) */
+    int iter, solver;                          /* 20, 2 */
+    int max_scales;                            /* 0 = until a side is <= 20 pixels (:108) */
+} pdegpu_flow_hs_params;
+void pdegpu_flow_hs_default_params(pdegpu_flow_hs_params *p);
+int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_hs_params *params);
+int pdegpu_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_hs_params *params);
+
 /* Iout = TVdenoise8(I_in)   matlab/denoising/TVdenoise8.m (BASELINE configs[3]: 8-neighbour anisotropic TV denoising):
  * two-level pyramid, outer_iter+1 lagged-diffusivity steps per level of ADdiffWeights -> TRACE/B -> PDEsolver8,
  * bilinear up-sampling. I_in: nrows x ncols x nframes single (as runme.m:118,144 passes it). */

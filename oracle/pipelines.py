@@ -160,3 +160,55 @@ def flow_fmg(I0, I1, backend, alpha=0.035, omega=1.9, firstLoop=4, iter=4, b1=0.
             U = ms.imresize_bicubic((U * up).astype(F32), output_size=size)
             V = ms.imresize_bicubic((V * up).astype(F32), output_size=size)
     return U, V
+
+
+def flow_hs(I0, I1, backend, alpha=0.2, omega=1.9, iter=20, b1=0.25, b2=0.75, scl_factor=0.75, solver=2, max_scales=None):
+    """[U V] = FlowEminHS_elin_2D_v10(cat(3, I0, I1), channels): Horn-Schunck (quadratic data and smoothness terms, one
+    linear solve per pyramid level), BASELINE configs[0]. I0, I1: rows x cols x channels, 0..255.
+    matlab/optical_flow/FlowEminHS_elin_2D_v10.m, line numbers in the comments."""
+    I0 = (np.asarray(I0, dtype=F32).reshape(I0.shape[0], I0.shape[1], -1) / F32(255)).astype(F32)     # :66
+    I1 = (np.asarray(I1, dtype=F32).reshape(I1.shape[0], I1.shape[1], -1) / F32(255)).astype(F32)
+    ch = I0.shape[2]
+    G = ms.fspecial_gaussian(5, 1.25)                                                                   # :88
+    It0, It1 = [I0], [I1]
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :96-115
+        n0, n1 = ms.imresize_bilinear(It0[-1], scale=scl_factor), ms.imresize_bilinear(It1[-1], scale=scl_factor)
+        It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+        It0.append(n0); It1.append(n1)
+        if n0.shape[0] <= 20 or n0.shape[1] <= 20:
+            It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+            break
+    # (with max_scales reached before the size test the last level stays unsmoothed, as in the driver)
+    pre = np.array([[0.037659, 0.249724, 0.439911, 0.249724, 0.037659]])
+    odx = np.array([[0.104550, 0.292315, 0.0, -0.292315, -0.104550]])
+    oxx = np.array([[0.232905, 0.002668, -0.471147, 0.002668, 0.232905]])
+    f = lambda A, h: ms.imfilter(A, h, "replicate", conv=True)
+    U = V = None
+    for s in range(len(It0) - 1, -1, -1):                                                               # :123
+        A0, A1 = It0[s], It1[s]
+        rows, cols = A0.shape[:2]
+        W = np.full((rows, cols), alpha * ch, dtype=np.float64).astype(F32)                             # :127
+        if U is None:
+            U = np.zeros((rows, cols), F32); V = np.zeros((rows, cols), F32)
+        Ist = ((A0 + A1).astype(F32) * F32(0.55)).astype(F32)                                           # :139
+        Idt = (A0 - A1).astype(F32)
+        Idx = f(f(Ist, pre.T), odx); Idy = f(f(Ist, pre), odx.T)                                        # :142-146
+        Idxx = f(f(Ist, pre.T), oxx); Idyy = f(f(Ist, pre), oxx.T)
+        Idxy = f(f(Ist, odx), odx.T)
+        Idxt = (f(f(A0, pre.T), odx) - f(f(A1, pre.T), odx)).astype(F32)                                # :148-154
+        Idyt = (f(f(A0, pre), odx.T) - f(f(A1, pre), odx.T)).astype(F32)
+        terms = ms.fmg_terms((Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy), b1, b2)                     # :159-163 (same formulas)
+        summed = []
+        for t in terms:                                                                                 # :168-172 sum(.,3)
+            acc = t[:, :, 0].copy()
+            for k in range(1, ch):
+                acc = (acc + t[:, :, k]).astype(F32)
+            summed.append(acc)
+        U, V = backend.call("Oflow_sor_elin4_2d", [U, V] + summed + [W, W, W, W, F32(iter), F32(omega), F32(solver)], 2)   # :174-188
+        if s > 0:                                                                                       # :193-196
+            up = F32(1.0 / scl_factor)
+            size = It0[s - 1].shape[:2]
+            U = ms.imresize_bicubic(ms.medfilt2_symmetric((U * up).astype(F32)), output_size=size)
+            V = ms.imresize_bicubic(ms.medfilt2_symmetric((V * up).astype(F32)), output_size=size)
+    return U, V

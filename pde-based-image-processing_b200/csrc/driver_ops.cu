@@ -696,12 +696,30 @@ fmg_terms_kernel(float *__restrict__ M, float *__restrict__ Cu, float *__restric
 }
 
 __global__ void __launch_bounds__(256)
-fmg_prescale_kernel(float *__restrict__ Ist, float *__restrict__ Idt, const float *__restrict__ I0, const float *__restrict__ I1, long long n)
+fmg_prescale_kernel(float *__restrict__ Ist, float *__restrict__ Idt, const float *__restrict__ I0, const float *__restrict__ I1, float div, long long n)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    Ist[t] = __fdiv_rn(mulf(addf(I0[t], I1[t]), 0.55f), 255.0f);
-    Idt[t] = __fdiv_rn(subf(I0[t], I1[t]), 255.0f);
+    Ist[t] = __fdiv_rn(mulf(addf(I0[t], I1[t]), 0.55f), div);
+    Idt[t] = __fdiv_rn(subf(I0[t], I1[t]), div);
+}
+
+// out = sum(in, 3) in single, channel after channel (FlowEminHS_elin_2D_v10.m:168-172)
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(float *__restrict__ out, const float *__restrict__ in, int channels, long long npix)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npix) return;
+    float acc = in[t];
+    for (int c = 1; c < channels; c++) acc = addf(acc, in[(long long)c * npix + t]);
+    out[t] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+fill_kernel(float *__restrict__ out, float v, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = v;
 }
 }  // namespace
 
@@ -714,10 +732,28 @@ int op_fmg_terms(pdegpu_ctx *ctx, float *const out[5], const float *const der[8]
     return PDEGPU_OK;
 }
 
-int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n)
+int op_channel_sum(pdegpu_ctx *ctx, float *out, const float *in, int channels, long long npix)
+{
+    PDEGPU_PROF(ctx, "channel_sum_kernel", 4.0 * npix * (channels + 1));
+    channel_sum_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, ctx->stream>>>(out, in, channels, npix);
+    PDEGPU_LAUNCH_CHECK(ctx, "channel_sum_kernel");
+    return PDEGPU_OK;
+}
+
+int op_fill(pdegpu_ctx *ctx, float *out, float v, long long n)
+{
+    PDEGPU_PROF(ctx, "fill_kernel", 4.0 * n);
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(out, v, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "fill_kernel");
+    return PDEGPU_OK;
+}
+
+// Ist = (I0+I1).*0.55/div, Idt = (I0-I1)/div: div = 255 in the FMG driver (FlowEminNDFASFMG_elin_2D_v10.m:124-125),
+// 1 in the Horn-Schunck driver, whose frames are already scaled (FlowEminHS_elin_2D_v10.m:139-140)
+int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n, float div)
 {
     PDEGPU_PROF(ctx, "fmg_prescale_kernel", 16.0 * n);
-    fmg_prescale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(Ist, Idt, I0, I1, n);
+    fmg_prescale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(Ist, Idt, I0, I1, div, n);
     PDEGPU_LAUNCH_CHECK(ctx, "fmg_prescale_kernel");
     return PDEGPU_OK;
 }

@@ -143,5 +143,7 @@ int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const fl
 int op_axpby_div(pdegpu_ctx *ctx, float *out, const float *x, float d, long long n);
 int op_ad_diff_weights(pdegpu_ctx *ctx, float *const w[8], float *TRACE, float *B, const float *D, const float *Iin, int nr, int nc, int frames, double quantile, double scale, double *lambda_dev, int wframes = 1);
 int op_fmg_terms(pdegpu_ctx *ctx, float *const out[5], const float *const der[8], float b1, float b2, long long n);
-int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n);
+int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n, float div = 255.0f);
+int op_channel_sum(pdegpu_ctx *ctx, float *out, const float *in, int channels, long long npix);
+int op_fill(pdegpu_ctx *ctx, float *out, float v, long long n);
 int imresize_2d(pdegpu_ctx *ctx, float *out, float *tmp, const float *in, int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes, int cubic);

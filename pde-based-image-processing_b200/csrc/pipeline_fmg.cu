@@ -143,6 +143,40 @@ struct Fmg {
     }
 };
 
+// Derivative stacks of one level, shared by the FMG driver (FlowEminNDFASFMG_elin_2D_v10.m:123-141: frames 0..255,
+// Ist and Idt divided by 255, temporal-derivative kernels O_dx/255) and the Horn-Schunck driver
+// (FlowEminHS_elin_2D_v10.m:139-154: frames already scaled, div = 1). der = Idt, Idx, Idy, Idxt, Idyt, Idxx, Idyy, Idxy.
+int derivative_stack(pdegpu_ctx *ctx, const Lvl &l, int C, float div, float *tmp, float *tmp2, float *Ist)
+{
+    static const double pre[5] = {0.037659, 0.249724, 0.439911, 0.249724, 0.037659};
+    // 'conv' = correlation with the flipped kernel
+    static const double odx_f[5] = {-0.104550, -0.292315, 0.0, 0.292315, 0.104550};                 // O_dx flipped
+    static const double oxx[5] = {0.232905, 0.002668, -0.471147, 0.002668, 0.232905};
+    double odxs_f[5];
+    for (int k = 0; k < 5; k++) odxs_f[k] = odx_f[k] / (double)div;                                 // O_dx_scl flipped
+    const long long n = (long long)l.n;
+    auto filt = [&](float *out, const float *in, const double *h, int kr, int kc) {
+        return op_imfilter(ctx, out, in, l.nr, l.nc, C, n, n, h, kr, kc, 1, 1.0f);
+    };
+    RC(op_fmg_prescale(ctx, Ist, l.der[0], l.It[0], l.It[1], n * C, div));                          // Ist, Idt
+    RC(filt(tmp, Ist, pre, 5, 1));                                                                  // prefilter_spa'
+    RC(filt(l.der[1], tmp, odx_f, 1, 5));                                                           // Idx
+    RC(filt(l.der[5], tmp, oxx, 1, 5));                                                             // Idxx
+    RC(filt(tmp, Ist, pre, 1, 5));                                                                  // prefilter_spa
+    RC(filt(l.der[2], tmp, odx_f, 5, 1));                                                           // Idy
+    RC(filt(l.der[6], tmp, oxx, 5, 1));                                                             // Idyy
+    RC(filt(tmp, Ist, odx_f, 1, 5));
+    RC(filt(l.der[7], tmp, odx_f, 5, 1));                                                           // Idxy
+    // Idxt = Idxt0 - Idxt1, Idyt = Idyt0 - Idyt1
+    RC(filt(tmp, l.It[0], pre, 5, 1)); RC(filt(l.der[3], tmp, odxs_f, 1, 5));
+    RC(filt(tmp, l.It[1], pre, 5, 1)); RC(filt(tmp2, tmp, odxs_f, 1, 5));
+    RC(op_axpby(ctx, l.der[3], 1.0f, l.der[3], -1.0f, tmp2, n * C));
+    RC(filt(tmp, l.It[0], pre, 1, 5)); RC(filt(l.der[4], tmp, odxs_f, 5, 1));
+    RC(filt(tmp, l.It[1], pre, 1, 5)); RC(filt(tmp2, tmp, odxs_f, 5, 1));
+    RC(op_axpby(ctx, l.der[4], 1.0f, l.der[4], -1.0f, tmp2, n * C));
+    return PDEGPU_OK;
+}
+
 // fspecial('gaussian', [5 5], sigma), column-major
 void gaussian5x5(double sigma, double *h)
 {
@@ -194,12 +228,6 @@ int fmg_run(pdegpu_ctx *ctx, Stack &b, float *Uout, float *Vout, const float *I0
         double G[25];
         gaussian5x5(1.0, G);                                                                        // :97
         static const double lpf[5] = {1 / 16.0, 4 / 16.0, 6 / 16.0, 4 / 16.0, 1 / 16.0};            // :98
-        static const double pre[5] = {0.037659, 0.249724, 0.439911, 0.249724, 0.037659};            // :82
-        // 'conv' = correlation with the flipped kernel
-        static const double odx_f[5] = {-0.104550, -0.292315, 0.0, 0.292315, 0.104550};             // O_dx flipped (:84)
-        double odxs_f[5];
-        for (int k = 0; k < 5; k++) odxs_f[k] = odx_f[k] / 255.0;                                   // O_dx_scl flipped (:85)
-        static const double oxx[5] = {0.232905, 0.002668, -0.471147, 0.002668, 0.232905};           // :88
         const float *Iin[2] = {I0, I1};
         for (int q = 0; q < 2; q++) {
             RC(op_imfilter(ctx, f.L[0].It[q], Iin[q], nrows, ncols, C, (long long)n0, (long long)n0, G, 5, 5, 1, 1.0f));   // :103-104
@@ -211,27 +239,8 @@ int fmg_run(pdegpu_ctx *ctx, Stack &b, float *Uout, float *Vout, const float *I0
         }
         for (int s = 0; s < S; s++) {                                                               // :123-149
             const Lvl &l = f.L[s];
-            const long long n = (long long)l.n;
-            auto filt = [&](float *out, const float *in, const double *h, int kr, int kc) {
-                return op_imfilter(ctx, out, in, l.nr, l.nc, C, n, n, h, kr, kc, 1, 1.0f);
-            };
-            RC(op_fmg_prescale(ctx, Ist, l.der[0], l.It[0], l.It[1], n * C));                       // Ist, Idt  :124-125
-            RC(filt(f.tmp, Ist, pre, 5, 1));                                                        // prefilter_spa'
-            RC(filt(l.der[1], f.tmp, odx_f, 1, 5));                                                 // Idx  :127
-            RC(filt(l.der[5], f.tmp, oxx, 1, 5));                                                   // Idxx :129
-            RC(filt(f.tmp, Ist, pre, 1, 5));                                                        // prefilter_spa
-            RC(filt(l.der[2], f.tmp, odx_f, 5, 1));                                                 // Idy  :128
-            RC(filt(l.der[6], f.tmp, oxx, 5, 1));                                                   // Idyy :130
-            RC(filt(f.tmp, Ist, odx_f, 1, 5));
-            RC(filt(l.der[7], f.tmp, odx_f, 5, 1));                                                 // Idxy :131
-            // Idxt = Idxt0 - Idxt1, Idyt = Idyt0 - Idyt1  (:133-139)
-            RC(filt(f.tmp, l.It[0], pre, 5, 1)); RC(filt(l.der[3], f.tmp, odxs_f, 1, 5));
-            RC(filt(f.tmp, l.It[1], pre, 5, 1)); RC(filt(f.tmp2, f.tmp, odxs_f, 1, 5));
-            RC(op_axpby(ctx, l.der[3], 1.0f, l.der[3], -1.0f, f.tmp2, n * C));
-            RC(filt(f.tmp, l.It[0], pre, 1, 5)); RC(filt(l.der[4], f.tmp, odxs_f, 5, 1));
-            RC(filt(f.tmp, l.It[1], pre, 1, 5)); RC(filt(f.tmp2, f.tmp, odxs_f, 5, 1));
-            RC(op_axpby(ctx, l.der[4], 1.0f, l.der[4], -1.0f, f.tmp2, n * C));
-            RC(op_fmg_terms(ctx, l.coef, l.der, (float)P.b1, (float)P.b2, n * C));                  // :143-149
+            RC(derivative_stack(ctx, l, C, 255.0f, f.tmp, f.tmp2, Ist));
+            RC(op_fmg_terms(ctx, l.coef, l.der, (float)P.b1, (float)P.b2, (long long)l.n * C));     // :143-149
         }
     }
 
@@ -314,6 +323,154 @@ extern "C" int pdegpu_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const flo
     PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(d0, I0, nimg, cudaMemcpyHostToDevice, ctx->stream));
     PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(d1, I1, nimg, cudaMemcpyHostToDevice, ctx->stream));
     rc = pdegpu_dev_flow_fmg_2d(ctx, dU, dV, d0, d1, nrows, ncols, channels, batch, params);
+    if (rc) return rc;
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(U, dU, nflow, cudaMemcpyDeviceToHost, ctx->stream));
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(V, dV, nflow, cudaMemcpyDeviceToHost, ctx->stream));
+    PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PDEGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Horn-Schunck, matlab/optical_flow/FlowEminHS_elin_2D_v10.m (BASELINE configs[0]): bilinear x0.75 pyramid with 5x5
+// Gaussian smoothing (:96-115), per level the derivative stacks and quadratic terms (:139-172), ONE linear solve
+// Oflow_sor_elin4_2d with constant weights alpha*channels (:127,174-188), median + bicubic up-sampling (:193-196).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int hs_run(pdegpu_ctx *ctx, Stack &b, float *Uout, float *Vout, const float *I0, const float *I1, int nrows, int ncols, int C,
+           const pdegpu_flow_hs_params &P)
+{
+    const bool dry = b.dry;
+    std::vector<Lvl> L;
+    {
+        Lvl l; memset(&l, 0, sizeof l);
+        l.nr = nrows; l.nc = ncols; l.n = (size_t)nrows * ncols;
+        L.push_back(l);
+        const int max_scales = P.max_scales > 0 ? P.max_scales : (1 << 30);
+        while ((int)L.size() < max_scales) {
+            Lvl n; memset(&n, 0, sizeof n);
+            n.nr = (int)ceil(L.back().nr * P.scl_factor); n.nc = (int)ceil(L.back().nc * P.scl_factor); n.n = (size_t)n.nr * n.nc;
+            L.push_back(n);
+            if (n.nr <= 20 || n.nc <= 20) break;
+        }
+    }
+    const int S = (int)L.size();
+    const bool last_smoothed = L[S - 1].nr <= 20 || L[S - 1].nc <= 20;       // the size test smooths the last level (:108-113)
+    if (L.back().nr < 5 || L.back().nc < 5) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "flow_hs: coarsest level smaller than 5 pixels");
+    const size_t n0 = L[0].n;
+    for (int s = 0; s < S; s++) for (int k = 0; k < 2; k++) L[s].It[k] = b.take(L[s].n * C);
+    Lvl w; memset(&w, 0, sizeof w);                                          // work arrays, finest-level size, reused per level
+    for (int k = 0; k < 8; k++) w.der[k] = b.take(n0 * C);
+    for (int k = 0; k < 5; k++) w.coef[k] = b.take(n0 * C);
+    float *T[5], *W = b.take(n0), *tmp = b.take(n0 * C), *tmp2 = b.take(n0 * C), *Ist = b.take(n0 * C);
+    for (int k = 0; k < 5; k++) T[k] = b.take(n0);
+    float *U = b.take(n0), *V = b.take(n0), *Us = b.take(n0), *Um = b.take(n0);
+    if (dry) return PDEGPU_OK;
+
+    double G[25];
+    gaussian5x5(1.25, G);                                                                           // :88
+    const float *Iin[2] = {I0, I1};
+    for (int q = 0; q < 2; q++) {
+        RC(op_axpby_div(ctx, L[0].It[q], Iin[q], 255.0f, (long long)(n0 * C)));                    // Iin = single(Iin)./255  (:66)
+        for (int s = 1; s < S; s++) {                                                               // next level from the UNSMOOTHED one (:97-104)
+            const Lvl &p = L[s - 1], &l = L[s];
+            RC(imresize_2d(ctx, l.It[q], tmp, p.It[q], p.nr, p.nc, l.nr, l.nc, P.scl_factor, P.scl_factor, 1, C, 0));
+            RC(op_imfilter(ctx, tmp2, p.It[q], p.nr, p.nc, C, (long long)p.n, (long long)p.n, G, 5, 5, 1, 1.0f));
+            PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(p.It[q], tmp2, p.n * C * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        if (last_smoothed && S > 1) {
+            const Lvl &l = L[S - 1];
+            RC(op_imfilter(ctx, tmp2, l.It[q], l.nr, l.nc, C, (long long)l.n, (long long)l.n, G, 5, 5, 1, 1.0f));
+            PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(l.It[q], tmp2, l.n * C * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    const float up = (float)(1.0 / P.scl_factor);
+    for (int s = S - 1; s >= 0; s--) {                                                              // :123
+        Lvl l = w;
+        l.nr = L[s].nr; l.nc = L[s].nc; l.n = L[s].n; l.It[0] = L[s].It[0]; l.It[1] = L[s].It[1];
+        const long long n = (long long)l.n;
+        if (s == S - 1) {
+            PDEGPU_CUDA_OK(ctx, cudaMemsetAsync(U, 0, l.n * sizeof(float), ctx->stream));
+            PDEGPU_CUDA_OK(ctx, cudaMemsetAsync(V, 0, l.n * sizeof(float), ctx->stream));
+        }
+        RC(op_fill(ctx, W, (float)(P.alpha * C), n));                                               // W = alpha*channels*ones (:127)
+        RC(derivative_stack(ctx, l, C, 1.0f, tmp, tmp2, Ist));                                      // :139-154
+        RC(op_fmg_terms(ctx, l.coef, l.der, (float)P.b1, (float)P.b2, n * C));                      // :159-163
+        for (int k = 0; k < 5; k++) RC(op_channel_sum(ctx, T[k], l.coef[k], C, n));                 // :168-172
+        pdegpu_system sys;
+        memset(&sys, 0, sizeof sys);
+        sys.family = PDEGPU_FLOW_ELIN4; sys.nrows = l.nr; sys.ncols = l.nc; sys.batch = 1; sys.batch_stride = n;
+        sys.x[0] = U; sys.x[1] = V;
+        sys.m = T[0]; sys.c[0] = T[1]; sys.c[1] = T[2]; sys.d[0] = T[3]; sys.d[1] = T[4];
+        for (int k = 0; k < 4; k++) sys.w[k] = W;
+        RC(pdegpu_dev_relax(ctx, &sys, P.iter, (float)P.omega, P.solver));                          // :174-188
+        if (s > 0) {                                                                                // :193-196
+            const Lvl &o = L[s - 1];
+            float *xs[2] = {U, V};
+            for (int q = 0; q < 2; q++) {
+                RC(op_axpby(ctx, Us, up, xs[q], 0.0f, nullptr, n));
+                RC(op_medfilt3(ctx, Um, Us, l.nr, l.nc, 1, n));
+                RC(imresize_2d(ctx, xs[q], tmp, Um, l.nr, l.nc, o.nr, o.nc, (double)o.nr / l.nr, (double)o.nc / l.nc, 1, 1, 1));
+            }
+        }
+    }
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(Uout, U, n0 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(Vout, V, n0 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    return PDEGPU_OK;
+}
+
+}  // namespace
+
+extern "C" void pdegpu_flow_hs_default_params(pdegpu_flow_hs_params *p)
+{
+    // defaults of FlowEminHS_elin_2D_v10.m:48-58
+    p->alpha = 0.2; p->omega = 1.9; p->b1 = 0.25; p->b2 = 0.75; p->scl_factor = 0.75;
+    p->iter = 20; p->solver = 2; p->max_scales = 0;
+}
+
+extern "C" int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_hs_params *params)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!U || !V || !I0 || !I1 || !params) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_flow_hs_2d: null pointer");
+    if (nrows < 8 || ncols < 8 || channels < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_dev_flow_hs_2d: bad shape");
+    if (!(params->scl_factor > 0.1 && params->scl_factor < 1.0)) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_flow_hs_2d: bad parameters");
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    Stack dry = {nullptr, 0, 0, true};
+    int rc = hs_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
+    if (rc) return rc;
+    if (dry.peak > ctx->work_bytes) {
+        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->work) cudaFree(ctx->work);
+        ctx->work = nullptr; ctx->work_bytes = 0;
+        if (cudaMalloc((void **)&ctx->work, dry.peak) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_flow_hs_2d: cannot allocate %zu bytes of workspace", dry.peak); }
+        ctx->work_bytes = dry.peak;
+    }
+    const size_t np = (size_t)nrows * ncols;
+    for (int bi = 0; bi < batch; bi++) {
+        Stack w = {ctx->work, 0, 0, false};
+        rc = hs_run(ctx, w, U + bi * np, V + bi * np, I0 + bi * np * channels, I1 + bi * np * channels, nrows, ncols, channels, *params);
+        if (rc) return rc;
+    }
+    return PDEGPU_OK;
+}
+
+extern "C" int pdegpu_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
+        int nrows, int ncols, int channels, int batch, const pdegpu_flow_hs_params *params)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    if (!U || !V || !I0 || !I1 || !params) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_flow_hs_2d: null pointer");
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t nimg = (size_t)nrows * ncols * channels * batch * sizeof(float), nflow = (size_t)nrows * ncols * batch * sizeof(float);
+    pdegpu_arena_reset(ctx);
+    int rc = pdegpu_arena_reserve(ctx, 2 * nimg + 2 * nflow + 4096);
+    if (rc) return rc;
+    float *d0 = (float *)pdegpu_arena_alloc(ctx, nimg), *d1 = (float *)pdegpu_arena_alloc(ctx, nimg);
+    float *dU = (float *)pdegpu_arena_alloc(ctx, nflow), *dV = (float *)pdegpu_arena_alloc(ctx, nflow);
+    if (!d0 || !d1 || !dU || !dV) return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_flow_hs_2d: arena exhausted");
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(d0, I0, nimg, cudaMemcpyHostToDevice, ctx->stream));
+    PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(d1, I1, nimg, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pdegpu_dev_flow_hs_2d(ctx, dU, dV, d0, d1, nrows, ncols, channels, batch, params);
     if (rc) return rc;
     PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(U, dU, nflow, cudaMemcpyDeviceToHost, ctx->stream));
     PDEGPU_CUDA_OK(ctx, cudaMemcpyAsync(V, dV, nflow, cudaMemcpyDeviceToHost, ctx->stream));

@@ -81,6 +81,12 @@ class FlowFmgParams(ctypes.Structure):
                 ("firstLoop", c_int), ("iter", c_int), ("solver", c_int), ("cycle_index", c_int), ("max_scales", c_int)]
 
 
+class FlowHsParams(ctypes.Structure):
+    """Mirror of `pdegpu_flow_hs_params`."""
+    _fields_ = [("alpha", ctypes.c_double), ("omega", ctypes.c_double), ("b1", ctypes.c_double), ("b2", ctypes.c_double),
+                ("scl_factor", ctypes.c_double), ("iter", c_int), ("solver", c_int), ("max_scales", c_int)]
+
+
 _dll = None
 
 
@@ -166,6 +172,11 @@ def dll() -> ctypes.CDLL:
         for fn in (L.pdegpu_dev_flow_fmg_2d, L.pdegpu_flow_fmg_2d):
             fn.restype = c_int
             fn.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 4 + [POINTER(FlowFmgParams)]
+        L.pdegpu_flow_hs_default_params.restype = None
+        L.pdegpu_flow_hs_default_params.argtypes = [POINTER(FlowHsParams)]
+        for fn in (L.pdegpu_dev_flow_hs_2d, L.pdegpu_flow_hs_2d):
+            fn.restype = c_int
+            fn.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 4 + [POINTER(FlowHsParams)]
         L.pdegpu_upload.restype = c_int
         L.pdegpu_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
         L.pdegpu_download.restype = c_int
@@ -274,27 +285,32 @@ class Context:
         V = np.stack([V[b].reshape((nr, nc), order="F") for b in range(B)])
         return (U[0], V[0]) if single else (U, V)
 
-    def flow_fmg(self, I0, I1, params: "FlowFmgParams | None" = None, **overrides):
+    def flow_hs(self, I0, I1, params: "FlowHsParams | None" = None, **overrides):
+        """[U V] = FlowEminHS_elin_2D_v10 (Horn-Schunck) for one pair or a batch, same conventions as flow_fmg."""
+        return self.flow_fmg(I0, I1, params, _hs=True, **overrides)
+
+    def flow_fmg(self, I0, I1, params: "FlowFmgParams | None" = None, _hs=False, **overrides):
         """[U V] = FlowEminNDFASFMG_elin_2D_v10 for one pair or a batch: I0, I1 numpy [rows, cols, channels] or
         [batch, rows, cols, channels], values 0..255. Host-pointer entry point (H2D, pipeline, D2H)."""
         import numpy as np
+        cls, dflt, run = ((FlowHsParams, dll().pdegpu_flow_hs_default_params, dll().pdegpu_flow_hs_2d) if _hs else
+                          (FlowFmgParams, dll().pdegpu_flow_fmg_default_params, dll().pdegpu_flow_fmg_2d))
         I0 = np.asarray(I0, dtype=np.float32)
         I1 = np.asarray(I1, dtype=np.float32)
         single = I0.ndim == 3
         if single:
             I0, I1 = I0[None], I1[None]
         B, nr, nc, C = I0.shape
-        p = params or FlowFmgParams()
+        p = params or cls()
         if params is None:
-            dll().pdegpu_flow_fmg_default_params(ctypes.byref(p))
+            dflt(ctypes.byref(p))
         for k, v in overrides.items():
             setattr(p, k, v)
         a0 = np.ascontiguousarray(np.stack([I0[b].reshape(-1, order="F") for b in range(B)]))
         a1 = np.ascontiguousarray(np.stack([I1[b].reshape(-1, order="F") for b in range(B)]))
         U = np.empty((B, nr * nc), dtype=np.float32)
         V = np.empty((B, nr * nc), dtype=np.float32)
-        self._chk(dll().pdegpu_flow_fmg_2d(self.h, U.ctypes.data, V.ctypes.data, a0.ctypes.data, a1.ctypes.data,
-                                           nr, nc, C, B, ctypes.byref(p)))
+        self._chk(run(self.h, U.ctypes.data, V.ctypes.data, a0.ctypes.data, a1.ctypes.data, nr, nc, C, B, ctypes.byref(p)))
         U = np.stack([U[b].reshape((nr, nc), order="F") for b in range(B)])
         V = np.stack([V[b].reshape((nr, nc), order="F") for b in range(B)])
         return (U[0], V[0]) if single else (U, V)

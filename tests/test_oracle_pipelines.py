@@ -41,3 +41,14 @@ def test_llin_restatement_recovers_flow():
     I0, I1, u, v = synth.image_pair(7, nr, nc, nframes=3, scale=255.0, max_flow=2.0)
     U, V = pipelines.flow_llin(I0.reshape(nr, nc, 3), I1.reshape(nr, nc, 3), backend())
     assert aee(U, V, u, v) < 0.25
+
+
+def test_hs_restatement_recovers_subpixel_flow():
+    """Horn-Schunck with the driver's alpha = 0.2 over-smooths frames scaled to 0..1 (the parameters are tuned for the
+    Middlebury pair of runme.m:74); with a weaker smoothness term the restatement must beat the zero flow clearly."""
+    nr, nc = 96, 128
+    I0, I1, u, v = synth.image_pair(31, nr, nc, nframes=3, scale=255.0, max_flow=0.8)
+    U, V = pipelines.flow_hs(I0.reshape(nr, nc, 3), I1.reshape(nr, nc, 3), backend(), alpha=0.002, iter=100)
+    assert U.dtype == np.float32 and np.isfinite(U).all()
+    e, mag = aee(U, V, u, v), float(np.mean(np.sqrt(u ** 2 + v ** 2)))
+    assert e < 0.8 * mag, f"AEE {e} for a mean displacement of {mag}"

@@ -1,5 +1,5 @@
 #!/bin/bash
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_sweeps.py tests/test_gpu_pipeline.py -x -q -m gpu < /dev/null 2>&1 | tail -15
-P="timeout 120 python tools/w2_probe.py 64"
-echo "== shipping lib, default";  $P < /dev/null 2>&1 | tail -2
+timeout 600 python -m pytest tests -x -q -m gpu < /dev/null 2>&1 | tail -5
+timeout 400 python bench.py < /dev/null > gpurun_out/bench_b1.json 2> gpurun_out/bench_b1.err; echo "bench rc $?"
+tail -c 600 gpurun_out/bench_b1.err
