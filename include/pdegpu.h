@@ -419,6 +419,25 @@ int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, 
 int pdegpu_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
         int nrows, int ncols, int channels, int batch, const pdegpu_flow_hs_params *params);
 
+/* U = DispEminND_llin_sym_2D(Il, Ir)   matlab/disparity/DispEminND_llin_sym_2D.m (BASELINE configs[3]: symmetric-
+ * constraint stereo): two disparity fields coupled by a symmetry term; pyramid, cross warps of images and disparities,
+ * derivatives, robust data + symmetry weights, DdiffWeights, Disp_sor_llin_sym4_2d, median, bilinear up-sampling.
+ * Il, Ir: nrows x ncols x channels per pair, values 0..255; U: nrows x ncols x 2 per pair (U(:,:,1) left -> right,
+ * U(:,:,2) right -> left). uint8_input != 0 keeps the pyramid in class uint8 (toolbox results rounded and saturated) as
+ * for the imread images runme.m:17-28 passes. Pairs of a batch run one after the other on the stream. */
+typedef struct pdegpu_disp_sym_params {
+    double alpha, beta, omega, b1, b2, scl_factor;   /* 0.035, 0.4, 1.9, 0.25, 0.72, 0.75 (:50-60) */
+    int firstLoop, secondLoop, iter, solver;         /* 3, 4, 4, 2 */
+    int max_scales;                                  /* 0 = until a side is <= 10 pixels (:99) */
+    int uint8_input;                                 /* 1 */
+    float oob_value;                                 /* value of out-of-image warps (NaN) */
+} pdegpu_disp_sym_params;
+void pdegpu_disp_sym_default_params(pdegpu_disp_sym_params *p);
+int pdegpu_dev_disp_sym_2d(pdegpu_ctx *ctx, float *U, const float *Il, const float *Ir,
+        int nrows, int ncols, int channels, int batch, const pdegpu_disp_sym_params *params);
+int pdegpu_disp_sym_2d(pdegpu_ctx *ctx, float *U, const float *Il, const float *Ir,
+        int nrows, int ncols, int channels, int batch, const pdegpu_disp_sym_params *params);
+
 /* Iout = TVdenoise8(I_in)   matlab/denoising/TVdenoise8.m (BASELINE configs[3]: 8-neighbour anisotropic TV denoising):
  * two-level pyramid, outer_iter+1 lagged-diffusivity steps per level of ADdiffWeights -> TRACE/B -> PDEsolver8,
  * bilinear up-sampling. I_in: nrows x ncols x nframes single (as runme.m:118,144 passes it). */

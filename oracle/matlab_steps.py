@@ -395,3 +395,26 @@ def fmg_terms(der, b1, b2):
     Du = b1 * Idx * Idx + b2 * (Idxx * Idxx + Idxy * Idxy)
     Dv = b1 * Idy * Idy + b2 * (Idxy * Idxy + Idyy * Idyy)
     return M, Cu, Cv, Du, Dv
+
+
+def interp2_rows(Vals, Xq):
+    """interp2(X, Y, Vals, Xq, Y) with X, Y = meshgrid(1:cols, 1:rows) and the query on the grid's own rows: linear
+    interpolation along each row at the 1-based column positions Xq, NaN outside [1, cols] (and for NaN queries).
+    DispEminND_llin_sym_2D.m:143-144. Toolbox function: parity unpinned; double arithmetic, result in the class of Vals."""
+    Vals = np.asarray(Vals)
+    rows, cols = Vals.shape
+    xq = np.asarray(Xq, dtype=np.float64)
+    ok = (xq >= 1.0) & (xq <= cols)
+    xs = np.where(ok, xq, 1.0)
+    j0 = np.minimum(np.floor(xs).astype(np.int64), cols - 1)          # 1-based left sample; the last column uses t = 1
+    t = xs - j0
+    r = np.arange(rows)[:, None]
+    v0 = Vals[r, j0 - 1].astype(np.float64)
+    v1 = Vals[r, j0].astype(np.float64)
+    out = v0 * (1.0 - t) + v1 * t
+    return np.where(ok, out, np.nan).astype(Vals.dtype)
+
+
+def round_uint8(A):
+    """class uint8 after a toolbox call (imresize, imfilter on uint8 images): round half away from zero, saturate."""
+    return np.clip(np.floor(np.asarray(A, dtype=np.float64) + 0.5), 0, 255).astype(F32)

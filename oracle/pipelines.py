@@ -212,3 +212,62 @@ def flow_hs(I0, I1, backend, alpha=0.2, omega=1.9, iter=20, b1=0.25, b2=0.75, sc
             U = ms.imresize_bicubic(ms.medfilt2_symmetric((U * up).astype(F32)), output_size=size)
             V = ms.imresize_bicubic(ms.medfilt2_symmetric((V * up).astype(F32)), output_size=size)
     return U, V
+
+
+def disp_sym(Il, Ir, backend, alpha=0.035, beta=0.4, omega=1.9, firstLoop=3, secondLoop=4, iter=4, b1=0.25, b2=0.72,
+             scl_factor=0.75, solver=2, max_scales=None, uint8_input=True, oob=np.nan):
+    """U = DispEminND_llin_sym_2D(Il, Ir): symmetric stereo, two disparity fields U(:,:,1) (left -> right) and U(:,:,2)
+    (right -> left) coupled by a symmetry term (BASELINE configs[3]). Il, Ir: rows x cols x channels, 0..255; with
+    uint8_input the pyramid is kept in class uint8 as for the imread images of runme.m:17-28 (toolbox results rounded).
+    matlab/disparity/DispEminND_llin_sym_2D.m, line numbers in the comments. Returns (U0, U1)."""
+    q = ms.round_uint8 if uint8_input else (lambda A: np.asarray(A, dtype=F32))
+    It0 = [q(np.asarray(Il, dtype=F32).reshape(Il.shape[0], Il.shape[1], -1))]                          # :86-87
+    It1 = [q(np.asarray(Ir, dtype=F32).reshape(Ir.shape[0], Ir.shape[1], -1))]
+    G = ms.fspecial_gaussian(3, 1.0)                                                                    # :81
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :89-103
+        n0, n1 = q(ms.imresize_bilinear(It0[-1], scale=scl_factor)), q(ms.imresize_bilinear(It1[-1], scale=scl_factor))
+        It0[-1], It1[-1] = q(ms.imfilter(It0[-1], G)), q(ms.imfilter(It1[-1], G))
+        It0.append(n0); It1.append(n1)
+        if n0.shape[0] <= 10 or n0.shape[1] <= 10:
+            break
+    S = len(It0)
+    pre = np.array([[0.037659, 0.249724, 0.439911, 0.249724, 0.037659]])
+    odx = np.array([[0.104550, 0.292315, 0.0, -0.292315, -0.104550]])
+    f = lambda A, h: ms.imfilter(A, h, "replicate", conv=True)
+    U0 = U1 = None
+    for s in range(S - 1, -1, -1):                                                                      # :111
+        rows, cols = It0[s].shape[:2]
+        Xg, Yg = np.meshgrid(np.arange(1, cols + 1, dtype=F32), np.arange(1, rows + 1, dtype=F32))
+        if U0 is None:
+            U0 = np.zeros((rows, cols), F32); U1 = np.zeros((rows, cols), F32)
+        srDiff = 2.0 * (1.0 / scl_factor) ** -s                                                         # :127 (scl = s + 1)
+        for _ in range(firstLoop):                                                                      # :133
+            It0w = backend.bilin(It0[s], (Xg + U1).astype(F32), Yg, oob)                                # :138-139
+            It1w = backend.bilin(It1[s], (Xg + U0).astype(F32), Yg, oob)
+            U0w = ms.interp2_rows(U0, Xg.astype(np.float64) + U1)                                       # :144-145 (double)
+            U1w = ms.interp2_rows(U1, Xg.astype(np.float64) + U0)
+            Idt0, Idx1, _ = backend.call("FstDerivatives5", [It0[s], It1w], 3)                          # :150-154
+            Idxt0, Idyt0, Idxx1, _, Idxy1 = backend.call("SndDerivatives5", [It0[s], It1w], 5)
+            Idt1, Idx0, _ = backend.call("FstDerivatives5", [It1[s], It0w], 3)
+            Idxt1, Idyt1, Idxx0, _, Idxy0 = backend.call("SndDerivatives5", [It1[s], It0w], 5)
+            Udt0 = ((U0 + U1w) * F32(0.5)).astype(F32)                                                  # :159-165
+            Udx1 = f(f(U1w, pre.T), odx)
+            Udt1 = ((U1 + U0w) * F32(0.5)).astype(F32)
+            Udx0 = f(f(U0w, pre.T), odx)
+            dU0 = np.zeros((rows, cols), F32); dU1 = np.zeros((rows, cols), F32)
+            for _ in range(secondLoop):                                                                 # :188
+                CuG0, DuG0 = ms.disp_sym_terms((Idt0, Idx1, Idxt0, Idyt0, Idxx1, Idxy1), dU0, Udt0, Udx1, b1, b2, alpha, beta, srDiff)
+                CuG1, DuG1 = ms.disp_sym_terms((Idt1, Idx0, Idxt1, Idyt1, Idxx0, Idxy0), dU1, Udt1, Udx0, b1, b2, alpha, beta, srDiff)
+                w0 = backend.call("DdiffWeights", [(U0 + dU0).astype(F32), F32(0.00001)], 4)            # :219-220 [wW wN wE wS]
+                w1 = backend.call("DdiffWeights", [(U1 + dU1).astype(F32), F32(0.00001)], 4)
+                dU0, dU1 = backend.call("Disp_sor_llin_sym4_2d", [U0, dU0, CuG0, DuG0] + list(w0) + [U1, dU1, CuG1, DuG1] + list(w1)
+                                        + [F32(iter), F32(omega), F32(solver)], 2)                       # :227-247
+            U0 = ms.medfilt2_symmetric((U0 + dU0).astype(F32))                                          # :255-256
+            U1 = ms.medfilt2_symmetric((U1 + dU1).astype(F32))
+        if s > 0:                                                                                       # :265-267
+            up = F32(1.0 / scl_factor)
+            size = It0[s - 1].shape[:2]
+            U0 = ms.imresize_bilinear((U0 * up).astype(F32), output_size=size)
+            U1 = ms.imresize_bilinear((U1 * up).astype(F32), output_size=size)
+    return U0, U1

@@ -356,6 +356,36 @@ warp_coords_kernel(float *__restrict__ X, float *__restrict__ Y, const float *__
     Y[p] = V ? addf((float)(i + 1), V[p]) : (float)(i + 1);
 }
 
+// out = interp2(X, Y, vals, X + shift, Y) on the grid's own rows (DispEminND_llin_sym_2D.m:144-145): linear interpolation
+// along j at the 1-based position (j+1) + shift, NaN outside [1, ncols]; double arithmetic
+__global__ void __launch_bounds__(256)
+interp_rows_kernel(float *__restrict__ out, const float *__restrict__ vals, const float *__restrict__ shift, int nr, int nc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= nr) return;
+    const long long p = (long long)j * nr + i;
+    const double xq = (double)(j + 1) + (double)shift[p];
+    float r = nanf("");
+    if (xq >= 1.0 && xq <= (double)nc) {
+        int j0 = (int)floor(xq);
+        if (j0 > nc - 1) j0 = nc - 1;
+        const double t = xq - (double)j0;
+        const double v0 = (double)vals[(long long)(j0 - 1) * nr + i], v1 = (double)vals[(long long)j0 * nr + i];
+        r = (float)(v0 * (1.0 - t) + v1 * t);
+    }
+    out[p] = r;
+}
+
+// class uint8 after a toolbox call: round half away from zero, saturate to 0..255
+__global__ void __launch_bounds__(256)
+round_uint8_kernel(float *__restrict__ x, long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double v = floor((double)x[t] + 0.5);
+    x[t] = (float)(v < 0.0 ? 0.0 : v > 255.0 ? 255.0 : v);
+}
+
 inline dim3 grid2(int nr, int nc, int planes) { return dim3((nr + 255) / 256, nc, planes); }
 
 }  // namespace
@@ -477,6 +507,22 @@ int op_warp_coords(pdegpu_ctx *ctx, float *X, float *Y, const float *U, const fl
     PDEGPU_PROF(ctx, "warp_coords_kernel", 16.0 * nr * nc * batch);
     warp_coords_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(X, Y, U, V, nr, nc, stride);
     PDEGPU_LAUNCH_CHECK(ctx, "warp_coords_kernel");
+    return PDEGPU_OK;
+}
+
+int op_interp_rows(pdegpu_ctx *ctx, float *out, const float *vals, const float *shift, int nr, int nc)
+{
+    PDEGPU_PROF(ctx, "interp_rows_kernel", 16.0 * nr * nc);
+    interp_rows_kernel<<<grid2(nr, nc, 1), 256, 0, ctx->stream>>>(out, vals, shift, nr, nc);
+    PDEGPU_LAUNCH_CHECK(ctx, "interp_rows_kernel");
+    return PDEGPU_OK;
+}
+
+int op_round_uint8(pdegpu_ctx *ctx, float *x, long long n)
+{
+    PDEGPU_PROF(ctx, "round_uint8_kernel", 8.0 * n);
+    round_uint8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, n);
+    PDEGPU_LAUNCH_CHECK(ctx, "round_uint8_kernel");
     return PDEGPU_OK;
 }
 

@@ -146,4 +146,6 @@ int op_fmg_terms(pdegpu_ctx *ctx, float *const out[5], const float *const der[8]
 int op_fmg_prescale(pdegpu_ctx *ctx, float *Ist, float *Idt, const float *I0, const float *I1, long long n, float div = 255.0f);
 int op_channel_sum(pdegpu_ctx *ctx, float *out, const float *in, int channels, long long npix);
 int op_fill(pdegpu_ctx *ctx, float *out, float v, long long n);
+int op_interp_rows(pdegpu_ctx *ctx, float *out, const float *vals, const float *shift, int nr, int nc);
+int op_round_uint8(pdegpu_ctx *ctx, float *x, long long n);
 int imresize_2d(pdegpu_ctx *ctx, float *out, float *tmp, const float *in, int in_rows, int in_cols, int out_rows, int out_cols, double scale_rows, double scale_cols, int antialias, int planes, int cubic);

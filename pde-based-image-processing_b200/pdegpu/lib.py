@@ -87,6 +87,14 @@ class FlowHsParams(ctypes.Structure):
                 ("scl_factor", ctypes.c_double), ("iter", c_int), ("solver", c_int), ("max_scales", c_int)]
 
 
+class DispSymParams(ctypes.Structure):
+    """Mirror of `pdegpu_disp_sym_params`."""
+    _fields_ = [("alpha", ctypes.c_double), ("beta", ctypes.c_double), ("omega", ctypes.c_double), ("b1", ctypes.c_double),
+                ("b2", ctypes.c_double), ("scl_factor", ctypes.c_double),
+                ("firstLoop", c_int), ("secondLoop", c_int), ("iter", c_int), ("solver", c_int),
+                ("max_scales", c_int), ("uint8_input", c_int), ("oob_value", c_float)]
+
+
 _dll = None
 
 
@@ -177,6 +185,11 @@ def dll() -> ctypes.CDLL:
         for fn in (L.pdegpu_dev_flow_hs_2d, L.pdegpu_flow_hs_2d):
             fn.restype = c_int
             fn.argtypes = [c_void_p] + [c_void_p] * 4 + [c_int] * 4 + [POINTER(FlowHsParams)]
+        L.pdegpu_disp_sym_default_params.restype = None
+        L.pdegpu_disp_sym_default_params.argtypes = [POINTER(DispSymParams)]
+        for fn in (L.pdegpu_dev_disp_sym_2d, L.pdegpu_disp_sym_2d):
+            fn.restype = c_int
+            fn.argtypes = [c_void_p] + [c_void_p] * 3 + [c_int] * 4 + [POINTER(DispSymParams)]
         L.pdegpu_upload.restype = c_int
         L.pdegpu_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_size_t]
         L.pdegpu_download.restype = c_int
@@ -284,6 +297,22 @@ class Context:
         U = np.stack([U[b].reshape((nr, nc), order="F") for b in range(B)])
         V = np.stack([V[b].reshape((nr, nc), order="F") for b in range(B)])
         return (U[0], V[0]) if single else (U, V)
+
+    def disp_sym(self, Il, Ir, **overrides):
+        """(U0, U1) = DispEminND_llin_sym_2D(Il, Ir) for one stereo pair: Il, Ir numpy [rows, cols(, channels)], 0..255."""
+        import numpy as np
+        Il = np.asarray(Il, dtype=np.float32); Ir = np.asarray(Ir, dtype=np.float32)
+        Il = Il.reshape(Il.shape[0], Il.shape[1], -1); Ir = Ir.reshape(Ir.shape[0], Ir.shape[1], -1)
+        nr, nc, C = Il.shape
+        p = DispSymParams()
+        dll().pdegpu_disp_sym_default_params(ctypes.byref(p))
+        for k, v in overrides.items():
+            setattr(p, k, v)
+        a0 = np.ascontiguousarray(Il.reshape(-1, order="F")); a1 = np.ascontiguousarray(Ir.reshape(-1, order="F"))
+        U = np.empty(2 * nr * nc, dtype=np.float32)
+        self._chk(dll().pdegpu_disp_sym_2d(self.h, U.ctypes.data, a0.ctypes.data, a1.ctypes.data, nr, nc, C, 1, ctypes.byref(p)))
+        U = U.reshape((nr, nc, 2), order="F")
+        return U[:, :, 0].copy(), U[:, :, 1].copy()
 
     def flow_hs(self, I0, I1, params: "FlowHsParams | None" = None, **overrides):
         """[U V] = FlowEminHS_elin_2D_v10 (Horn-Schunck) for one pair or a batch, same conventions as flow_fmg."""

@@ -112,9 +112,9 @@ def pde_system(seed, nrows, ncols, nframes=1, eight=False, nan_frac=0.01):
     return s
 
 
-def image_pair(seed, nrows, ncols, nframes=1, scale=1.0, max_flow=3.0):
+def image_pair(seed, nrows, ncols, nframes=1, scale=1.0, max_flow=3.0, horizontal=False):
     """Smooth random texture and a second frame shifted by a known smooth flow (u along columns,
-    v along rows), sampled analytically so the pair is exact."""
+    v along rows), sampled analytically so the pair is exact. horizontal: v = 0 (a stereo pair)."""
     rng = np.random.default_rng(seed)
     ii, jj = np.meshgrid(np.arange(nrows, dtype=np.float64), np.arange(ncols, dtype=np.float64), indexing="ij")
     waves = [(rng.uniform(2, 30) * 2 * np.pi / ncols, rng.uniform(2, 30) * 2 * np.pi / nrows,
@@ -128,6 +128,8 @@ def image_pair(seed, nrows, ncols, nframes=1, scale=1.0, max_flow=3.0):
 
     u = max_flow * (0.5 * (jj / ncols - 0.5) + 0.3 * np.sin(2 * np.pi * ii / nrows))
     v = max_flow * (0.4 * (ii / nrows - 0.5) + 0.3 * np.cos(2 * np.pi * jj / ncols))
+    if horizontal:
+        v = np.zeros_like(u)
     I0 = np.stack([tex(jj, ii, k) for k in range(nframes)], axis=2)
     I1 = np.stack([tex(jj - u, ii - v, k) for k in range(nframes)], axis=2)
     lo, hi = I0.min(), I0.max()

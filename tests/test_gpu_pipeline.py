@@ -182,3 +182,33 @@ def test_hs_driver_iteration_counts(ctx):
     Uo, Vo = pipelines.flow_hs(I0, I1, backend(), iter=100, alpha=0.002)
     eg, eo = epe(Ug, Vg, u, v), epe(Uo, Vo, u, v)
     assert abs(eg - eo) < 0.02, f"AEE vs ground truth at iter=100, alpha=0.002: GPU {eg}, reference {eo}"
+
+
+# ---- DispEminND_llin_sym_2D (BASELINE configs[3]): symmetric-constraint stereo ----
+def stereo_pair(seed, nr, nc, C, max_disp=3.0):
+    I0, I1, u, _ = synth.image_pair(seed, nr, nc, nframes=C, scale=255.0, max_flow=max_disp, horizontal=True)
+    return I0.reshape(nr, nc, C), I1.reshape(nr, nc, C), u
+
+
+@pytest.mark.parametrize("C,u8", [(1, 1), (3, 0)])
+def test_disp_sym_converged_solves_match_reference(ctx, C, u8):
+    nr, nc = 96, 128
+    Il, Ir, _ = stereo_pair(41, nr, nc, C)
+    kw = dict(iter=150, omega=1.3, firstLoop=2, secondLoop=2, uint8_input=u8)
+    g0, g1 = ctx.disp_sym(Il, Ir, **kw)
+    o0, o1 = pipelines.disp_sym(Il, Ir, backend(), **kw)
+    assert np.array_equal(np.isnan(g0), np.isnan(o0)) and np.array_equal(np.isnan(g1), np.isnan(o1))
+    e = float(np.nanmean(np.abs(g0 - o0)) + np.nanmean(np.abs(g1 - o1)))
+    assert e < 1e-3, f"mean |GPU - reference| over both disparity fields {e}"
+
+
+def test_disp_sym_default_parameters_quality(ctx):
+    nr, nc = 120, 160
+    Il, Ir, u = stereo_pair(42, nr, nc, 3)
+    g0, g1 = ctx.disp_sym(Il, Ir)
+    o0, o1 = pipelines.disp_sym(Il, Ir, backend())
+    s = (slice(10, -10), slice(10, -10))
+    eg = float(np.nanmean(np.abs(g0[s] - u[s]))); eo = float(np.nanmean(np.abs(o0[s] - u[s])))
+    assert abs(eg - eo) < 0.02 and eg < 0.2, f"mean abs disparity error: GPU {eg}, reference {eo}"
+    # symmetry: the right -> left field mirrors the left -> right one
+    assert float(np.nanmean(np.abs(g1[s] + u[s]))) < 0.2

@@ -52,3 +52,20 @@ def test_hs_restatement_recovers_subpixel_flow():
     assert U.dtype == np.float32 and np.isfinite(U).all()
     e, mag = aee(U, V, u, v), float(np.mean(np.sqrt(u ** 2 + v ** 2)))
     assert e < 0.8 * mag, f"AEE {e} for a mean displacement of {mag}"
+
+
+def test_disp_sym_restatement_recovers_disparity():
+    nr, nc = 96, 128
+    Il, Ir, u, _ = synth.image_pair(41, nr, nc, nframes=3, scale=255.0, max_flow=3.0, horizontal=True)
+    U0, U1 = pipelines.disp_sym(Il, Ir, backend())
+    s = (slice(10, -10), slice(10, -10))
+    assert float(np.nanmean(np.abs(U0[s] - u[s]))) < 0.05 and float(np.nanmean(np.abs(U1[s] + u[s]))) < 0.05
+
+
+def test_interp2_rows_matches_definition():
+    from oracle import matlab_steps as ms
+    V = np.arange(12, dtype=np.float32).reshape(3, 4)          # rows x cols, value = 4*i + j
+    Xq = np.array([[1.0, 2.5, 4.0, 4.01], [0.99, 1.25, 3.75, np.nan], [1.0, 1.0, 4.0, 2.0]])
+    out = ms.interp2_rows(V, Xq)
+    exp = np.array([[0.0, 1.5, 3.0, np.nan], [np.nan, 4.25, 6.75, np.nan], [8.0, 8.0, 11.0, 9.0]], dtype=np.float32)
+    assert np.array_equal(np.isnan(out), np.isnan(exp)) and np.allclose(np.nan_to_num(out), np.nan_to_num(exp))
