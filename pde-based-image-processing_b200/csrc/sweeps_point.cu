@@ -27,7 +27,10 @@ __device__ __forceinline__ float f4c(const float4 &v, int k) { return k == 0 ? v
 // ALIGNED is a compile-time flag: a run-time one makes ptxas predicate the vector and the scalar loads into one
 // instruction stream, where the (predicated-off) scalar loads wait for the vector loads that share their registers.
 template <int FAM, bool ALIGNED>
-__global__ void __launch_bounds__(256, 2)
+#ifndef PDEGPU_PT_MINB
+#define PDEGPU_PT_MINB 2
+#endif
+__global__ void __launch_bounds__(256, PDEGPU_PT_MINB)
 rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega)
 {
     using F = Fam<FAM>;

@@ -33,12 +33,15 @@ __device__ __forceinline__ void st_release(unsigned *p, unsigned v)
 // warp vote: a lane-0-only spin leaves lane 0 and lanes 1..31 on separate control-flow paths, and the compiler may
 // keep them apart for the rest of the loop body, issuing every instruction twice (seen in ncu: avg 16 threads per
 // instruction, 2x instruction count). A wait that never ends is a scheduling bug: trap instead of hanging the GPU.
+#ifndef PDEGPU_POLL_NS
+#define PDEGPU_POLL_NS 100
+#endif
 __device__ __forceinline__ void warp_wait_ge(const unsigned *p, unsigned want, int lane)
 {
     (void)lane;
     unsigned spins = 0;
     while (!__all_sync(0xffffffffu, ld_acquire(p) >= want)) {
-        __nanosleep(100);
+        __nanosleep(PDEGPU_POLL_NS);
         if (++spins > (1u << 23)) __trap();
     }
 }

@@ -1,5 +1,7 @@
 #!/bin/bash
 cd /root/repo
-timeout 600 python -m pytest tests -x -q -m gpu < /dev/null 2>&1 | tail -5
-timeout 400 python bench.py < /dev/null > gpurun_out/bench_b1.json 2> gpurun_out/bench_b1.err; echo "bench rc $?"
-tail -c 600 gpurun_out/bench_b1.err
+timeout 600 python -m pytest tests -x -q -m gpu < /dev/null 2>&1 | tail -4
+timeout 500 python bench.py < /dev/null > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; echo "bench rc $?"
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 < /dev/null > gpurun_out/bench_c1_ref.json 2> gpurun_out/bench_c1_ref.err; echo "ref rc $?"
+timeout 300 python bench.py --solver 1 --flow-batch 0 --fmg-pairs 0 < /dev/null > gpurun_out/bench_c1_point.json 2> gpurun_out/bench_c1_point.err; echo "point rc $?"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" < /dev/null 2>&1 | tail -2

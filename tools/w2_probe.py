@@ -29,19 +29,22 @@ sysd = lib.make_system(lib.FLOW_LLIN4, NR, NC, batch=B, batch_stride=NR * NC,
                        w=[d[k].data_ptr() for k in ("wW", "wN", "wE", "wS")])
 L = lib.dll()
 out = (ctypes.c_ulonglong * 16)()
-have = hasattr(L, "pdegpu_debug_w2_probe")
-ctx.relax(sysd, 1, 1.9, 2)
+GEN3 = False
+probe_fn = getattr(L, "pdegpu_debug_w2_probe", None)
+have = probe_fn is not None
+SOLVER = int(os.environ.get('W2_SOLVER', '2'))
+ctx.relax(sysd, 1, 1.9, SOLVER)
 ctx.sync()
 if have:
-    L.pdegpu_debug_w2_probe(out)            # discard the warm-up pass
+    probe_fn(out)            # discard the warm-up pass
 ctx.profile(True)
-ctx.relax(sysd, 4, 1.9, 2)
+ctx.relax(sysd, 4, 1.9, SOLVER)
 ctx.sync()
 if have:
-    L.pdegpu_debug_w2_probe(out)
+    probe_fn(out)
 v = [int(x) for x in out]
 an = ("other", "wait freed buffer", "wait ring slot", "load issue", "wait solved (odd)", "wait loads", "rows + st.shared")
-sn = ("other", "wait filled buffer", "pick-up + solve + ring", "block write-out")
+sn = ("other", "wait filled buffer", "pick-up + solve", "ring write (+ wait odd readers)", "stores to X_out") if GEN3 else ("other", "wait filled buffer", "pick-up + solve + ring", "block write-out")
 if not have:
     v = [0] * 16
 print("assembler warps: total cycles", v[7])
