@@ -48,6 +48,15 @@ METRIC = "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, ALR)"
 UNIT = "Mpix*iter/s"
 
 
+_RESULT_FD = None
+
+
+def emit(text):
+    """the one result line, on the real stdout"""
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (text + "\n").encode())
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -184,7 +193,7 @@ def run_reference(args):
             t_all += dt
     v = float(np.mean(vals))
     r["value"] = v
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -433,7 +442,7 @@ def run_band(args):
             roof = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "peak_source": peak_src, "traffic": None, "launch_ms_avg": top["ms_total"] / top["launches"],
                     "launches": top["launches"], "algorithmic_bytes_per_launch": top["bytes_total"] / top["launches"]}
-        print(json.dumps({
+        emit(json.dumps({
             "metric": "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, red-black point SOR, one image in column bands)",
             "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -597,7 +606,7 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -605,6 +614,12 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there (NCCL's version banner under
+    # torchrun, for instance) is sent to stderr for the duration of the run
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "band":
