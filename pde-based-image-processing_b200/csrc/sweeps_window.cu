@@ -286,7 +286,7 @@ int window_pass(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const xout[2],
     p.NB = (sys->ncols + 7) / 8; p.TB = p.NB * sys->batch;
     p.R = g.R; p.D = g.D;
     p.omega = omega;
-    p.prefetch = 0;
+    p.G = 1;
     bool al = (sys->ncols % 4 == 0) && (ostride % 4 == 0);
     for (int q = 0; q < F::NUNK; q++) al = al && ((uintptr_t)xout[q] % 16 == 0);
     p.vec_ok = al ? 1 : 0;

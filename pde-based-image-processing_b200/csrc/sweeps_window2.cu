@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int kW2Threads = 384;
+constexpr int kW2MaxG = 4;                                   // at most 4 assembler warps per line
 
 // Phase probes (build with -DW2_PROBE; never in the shipped library): cycles per warp role, summed over all warps.
 #ifdef W2_PROBE
@@ -51,7 +52,6 @@ alr_window2_kernel(const WinParams p)
     // VW 4 single-buffered 395 / 448, VW 2 double-buffered 411 / 542 (same bytes in flight per lane -- the register file
     // is the limit -- and twice the load instructions).
     constexpr int VW = 4;
-    constexpr bool DOUBLE = VW == 2;
     constexpr int NT = (LS + 32 * VW - 1) / (32 * VW);
     constexpr int BUF = RF::N * LS;                           // floats per row buffer
     extern __shared__ float smem[];
@@ -61,8 +61,8 @@ alr_window2_kernel(const WinParams p)
     float *bufs = ring + (size_t)R * SP;
     unsigned *flags = reinterpret_cast<unsigned *>(bufs + (size_t)NBUF * BUF);
     unsigned *solved_seq = flags, *written_seq = flags + R, *block_cnt = flags + R + NBR;
-    unsigned *filled_seq = flags + R + 2 * NBR, *freed_seq = filled_seq + NBUF;
-    for (int t = threadIdx.x; t < R + 2 * NBR + 2 * NBUF; t += blockDim.x) flags[t] = 0;
+    unsigned *filled_seq = flags + R + 2 * NBR, *freed_seq = filled_seq + kW2MaxG * NBUF;
+    for (int t = threadIdx.x; t < R + 2 * NBR + (kW2MaxG + 1) * NBUF; t += blockDim.x) flags[t] = 0;
     __syncthreads();
 
     const int n = p.n, nlines = p.nlines;
@@ -95,48 +95,28 @@ alr_window2_kernel(const WinParams p)
 
     if (warp < NA) {
         // =============================== assembler warps ===============================
-        // A lane owns VW consecutive pixels of a batch (batch t = elements 32*VW*t ..). Two batches are in flight:
-        // the loads of batch t+1 (or of the first batch of this warp's next line) are issued before batch t is
-        // touched, so a line costs one exposed memory latency instead of one per batch.
+        // G warps share one line: warp h of a group takes the batches t = h, h+G, ... (a lane owns VW consecutive pixels
+        // of a batch, batch t = elements 32*VW*t ..). A row buffer is then held for 1/G of the time during assembly, and
+        // only NA/G lines are in assembly at once, so the other buffers decouple the assemblers from the solvers.
+        // The loads of a warp's next batch (or of its first batch of the group's next line) are issued as soon as the
+        // registers of the current one are free.
         PROBE_DECL;
-        RawBatch<FAM, VW> rawA, rawB;
+        RawBatch<FAM, VW> rawA;
         WinTask T, Tn;
-        int q = warp;
+        const int G = p.G, NG = NA / G, h = warp % G;
+        int q = warp / G;
         bool valid = q < Q && decode(q, T);
         auto first_el = [&](int t, int &e0, int &ec) { e0 = 32 * VW * t + VW * lane; ec = min(e0, ec_last); };
         auto issue_to = [&](RawBatch<FAM, VW> &rb, const WinTask &TT, int t) {
             int e0, ec;
             first_el(t, e0, ec);
-            if (e0 < LS) rb.template issue<AL>(s, TT, ec, n);
+            if (t < NT && e0 < LS) rb.template issue<AL>(s, TT, ec, n);
         };
-        // Optional L2 prefetch of a whole line two of this warp's lines ahead, one bulk-prefetch instruction per field
-        // (lane f = field f). OFF by default: measured on B200 it does not shorten the assemblers' load wait (24.6 % of
-        // their cycles with and without) and the pass gets slower (480 vs 413 us, lines of 480) -- the wait is not a DRAM
-        // round trip that L2 residency would remove. Kept behind PDEGPU_W2_PREFETCH=1 for the next look with ncu.
-        auto prefetch_line = [&](const WinTask &TT) {
-            if (!AL || !p.prefetch) return;
-            const float *f = nullptr;
-#pragma unroll
-            for (int k = 0; k < NUNK; k++) {
-                if (lane == k) f = s.x[k];
-                if (F::LATE && lane == 2 + k) f = s.x0[k];
-                if (lane == 4 + k) f = s.c[k];
-                if (lane == 6 + k) f = s.d[k];
-            }
-            if (NUNK == 2 && lane == 8) f = s.m;
-#pragma unroll
-            for (int k = 0; k < (F::EIGHT ? 8 : 4); k++) if (lane == 9 + k) f = s.w[k];
-            if (f) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f + TT.ibase), "r"(n * 4) : "memory");
-        };
-        if (valid) issue_to(rawA, T, 0);
-        for (; q < Q; q += NA) {
+        if (valid) issue_to(rawA, T, h);
+        for (; q < Q; q += NG) {
             const int bi = q % NBUF;
             const unsigned use = (unsigned)(q / NBUF);
-            const bool validn = q + NA < Q && decode(q + NA, Tn);
-            {
-                WinTask Tp;
-                if (q + 2 * NA < Q && decode(q + 2 * NA, Tp)) prefetch_line(Tp);
-            }
+            const bool validn = q + NG < Q && decode(q + NG, Tn);
             PROBE(0);
             warp_wait_ge(&freed_seq[bi], use, lane);          // the buffer's previous rows have been picked up
             PROBE(1);
@@ -182,54 +162,27 @@ alr_window2_kernel(const WinParams p)
                         stv(rs + P + e0, xo1);
                     }
                 };
-                if (DOUBLE) {
 #pragma unroll 1
-                    for (int t = 0; t < NT; t += 2) {
-                        PROBE(0);
-                        if (t + 1 < NT) issue_to(rawB, T, t + 1);
-                        PROBE(3);
-                        if (t == 0 && T.odd) {
-                            warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
-                            if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
-                        }
-                        PROBE(4);
-                        PROBE_USE(rawA.w4[0].v[0]); PROBE_USE(rawA.XO4[0].v[0]);
-                        PROBE(5);
-                        rows_of(rawA, t);
-                        PROBE(6);
-                        // next user of rawA: batch t+2 of this line, or the first batch of this warp's next line
-                        if (t + 2 < NT) issue_to(rawA, T, t + 2);
-                        else if (validn) issue_to(rawA, Tn, 0);
-                        PROBE(3);
-                        if (t + 1 < NT) {
-                            PROBE_USE(rawB.w4[0].v[0]); PROBE_USE(rawB.XO4[0].v[0]);
-                            PROBE(5);
-                            rows_of(rawB, t + 1);
-                            PROBE(6);
-                        }
+                for (int t = h; t < NT; t += G) {
+                    PROBE(0);
+                    if (t == h && T.odd) {                    // new values of the even neighbours
+                        warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
+                        if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
                     }
-                } else {
-#pragma unroll 1
-                    for (int t = 0; t < NT; t++) {
-                        PROBE(0);
-                        if (t == 0 && T.odd) {
-                            warp_wait_ge(&solved_seq[(l - 1) % R], (unsigned)l, lane);
-                            if (T.eE) warp_wait_ge(&solved_seq[(l + 1) % R], (unsigned)l + 2, lane);
-                        }
-                        PROBE(4);
-                        PROBE_USE(rawA.w4[0].v[0]); PROBE_USE(rawA.XO4[0].v[0]);
-                        PROBE(5);
-                        rows_of(rawA, t);
-                        PROBE(6);
-                        // the batch is consumed: its registers take the next one (of this line, or of this warp's next line)
-                        if (t + 1 < NT) issue_to(rawA, T, t + 1);
-                        else if (validn) issue_to(rawA, Tn, 0);
-                        PROBE(3);
-                    }
+                    PROBE(4);
+                    PROBE_USE(rawA.w4[0].v[0]); PROBE_USE(rawA.XO4[0].v[0]);
+                    PROBE(5);
+                    rows_of(rawA, t);
+                    PROBE(6);
+                    // the batch is consumed: its registers take the next one (of this line, or of the group's next line)
+                    if (t + G < NT) issue_to(rawA, T, t + G);
+                    else if (validn) issue_to(rawA, Tn, h);
+                    PROBE(3);
                 }
-            } else if (validn) issue_to(rawA, Tn, 0);
+                if (h >= NT && validn) issue_to(rawA, Tn, h);
+            } else if (validn) issue_to(rawA, Tn, h);
             __syncwarp();
-            if (lane == 0) st_release(&filled_seq[bi], use + 1);
+            if (lane == 0) st_release(&filled_seq[bi * kW2MaxG + h], use + 1);
             __syncwarp();
             T = Tn; valid = validn;
         }
@@ -243,7 +196,7 @@ alr_window2_kernel(const WinParams p)
             WinTask T;
             const bool valid = decode(q, T);
             PROBE(0);
-            warp_wait_ge(&filled_seq[bi], use + 1, lane);
+            for (int g = 0; g < p.G; g++) warp_wait_ge(&filled_seq[bi * kW2MaxG + g], use + 1, lane);
             PROBE(1);
             if (!valid) {
                 if (lane == 0) st_release(&freed_seq[bi], use + 1);
@@ -355,15 +308,16 @@ int window2_dispatch(pdegpu_ctx *ctx, WinParams &p, int M, int nunk, int batch)
     static const int envNA = getenv("PDEGPU_W2_NA") ? atoi(getenv("PDEGPU_W2_NA")) : 8;       // tuning overrides (NA + NS <= 12)
     static const int envNS = getenv("PDEGPU_W2_NS") ? atoi(getenv("PDEGPU_W2_NS")) : 4;
     p.NA = envNA; p.NS = envNS;
-    static const int envPF = getenv("PDEGPU_W2_PREFETCH") ? atoi(getenv("PDEGPU_W2_PREFETCH")) : 0;
-    p.prefetch = envPF;
+    static const int envG = getenv("PDEGPU_W2_G") ? atoi(getenv("PDEGPU_W2_G")) : 2;          // assembler warps per line
+    p.G = envG;
+    if (p.G < 1 || p.G > kW2MaxG || p.NA % p.G) return PDEGPU_ERR_UNSUPPORTED;
     if (p.NA < 1 || p.NS < 1 || p.NA + p.NS > kW2Threads / 32) return PDEGPU_ERR_UNSUPPORTED;
     static const int envR = getenv("PDEGPU_W2_R") ? atoi(getenv("PDEGPU_W2_R")) : 0;          // ring lines (multiple of 8) / even lead
     static const int envD = getenv("PDEGPU_W2_D") ? atoi(getenv("PDEGPU_W2_D")) : 0;
     static const int envNBUF = getenv("PDEGPU_W2_NBUF") ? atoi(getenv("PDEGPU_W2_NBUF")) : 8;
     const int RD[][2] = {{envR ? envR : 32, envD ? envD : 5}, {24, 4}, {16, 3}};
     for (auto &rd : RD) {
-        const size_t fixed = ((size_t)rd[0] * SP + rd[0] + 2 * (rd[0] / 8) + 32) * sizeof(float);
+        const size_t fixed = ((size_t)rd[0] * SP + rd[0] + 2 * (rd[0] / 8) + (kW2MaxG + 1) * 16) * sizeof(float);
         if (fixed >= room) continue;
         int nbuf = (int)((room - fixed) / ((size_t)rowf * LS * sizeof(float)));
         if (nbuf > envNBUF) nbuf = envNBUF;

@@ -15,7 +15,7 @@ struct WinParams {
     int NA, NS, NBUF;      // two-stage kernel: assembler warps, solver warps, row buffers
     int vec_ok;            // float4 stores of X_out are aligned
     int aligned;           // float4 loads of the inputs are aligned (else 4 scalar loads per vector)
-    int prefetch;          // two-stage kernel: L2 bulk prefetch of whole lines ahead of the assemblers
+    int G;                 // two-stage kernel: assembler warps per line
     float omega;
 };
 
