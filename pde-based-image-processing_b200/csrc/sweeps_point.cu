@@ -202,6 +202,185 @@ rb_tile_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, floa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same sweep with every operand staged through shared memory by cp.async (aligned problems only).
+// rb_tile_kernel keeps the coefficients of a thread's 4 pixels in registers from the first instruction to the last
+// (36 + 11 registers), which holds it at 126 registers = 2 CTAs per SM: when both CTAs compute, nothing is in flight
+// (ncu: 24 % occupancy, long_scoreboard 4.6, DRAM 45 % busy). Here a CTA fires all its copies (unknown tile + halo,
+// coefficient tile, ring coefficients) without holding a register, waits once, and computes out of shared memory.
+// Measured (B200, 64 x 480x640 llin4, us per sweep): register-staged 319, cp.async with 2 CTAs per SM 311, with 3 CTAs
+// per SM (80 registers, 192 B of spills) 365 -- the sweep is bound by the per-warp instruction latency of the update
+// (~640 instructions per thread and tile, 16 warps per SM), not by the bytes in flight; kept because it is the faster one.
+// Same ordering, same point_formula, same bits as rb_tile_kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *sm, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *sm, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(sm)), "l"(g) : "memory");
+}
+
+constexpr int PT_RING = 144;                                  // ring pixels (138) padded
+
+template <int FAM> constexpr int pt_async_floats()
+{
+    using F = Fam<FAM>;
+    return F::NUNK * (F::LATE ? 2 : 1) * PS_J * PS_I + (4 + 2 * F::NUNK + (F::NUNK == 2 ? 1 : 0)) * (PT_J * PT_I + PT_RING);
+}
+
+#ifndef PDEGPU_PTA_MINB
+#define PDEGPU_PTA_MINB 2
+#endif
+template <int FAM>
+__global__ void __launch_bounds__(256, PDEGPU_PTA_MINB)
+rb_tile_async_kernel(SysView s, float *__restrict__ xo0, float *__restrict__ xo1, float omega)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK;
+    constexpr int NF = NUNK * (F::LATE ? 2 : 1);              // x[q], then x0[q]
+    constexpr int NC = 4 + 2 * NUNK + (NUNK == 2 ? 1 : 0);    // w[0..3], C[q], D[q], M
+    constexpr int CI_C = 4, CI_D = 4 + NUNK, CI_M = 4 + 2 * NUNK;
+    extern __shared__ __align__(16) float dsm[];
+    float (*sm)[PS_J][PS_I] = reinterpret_cast<float (*)[PS_J][PS_I]>(dsm);
+    float (*cf)[PT_J][PT_I] = reinterpret_cast<float (*)[PT_J][PT_I]>(dsm + NF * PS_J * PS_I);
+    float *rg = dsm + NF * PS_J * PS_I + NC * PT_J * PT_I;    // ring coefficients: rg[f * PT_RING + tid]
+    const int nr = s.nrows, nc = s.ncols;
+    const int i0 = blockIdx.x * PT_I, j0 = blockIdx.y * PT_J;
+    const long long base = (long long)blockIdx.z * s.bstride;
+    const int tid = threadIdx.x;
+    const float *fld[4] = {s.x[0] + base, NUNK == 2 ? s.x[1] + base : nullptr,
+                           F::LATE ? s.x0[0] + base : nullptr, (F::LATE && NUNK == 2) ? s.x0[1] + base : nullptr};
+    auto field = [&](int f) -> const float * { return fld[f < NUNK ? f : 2 + (NUNK == 2 ? f - NUNK : 0)]; };
+    const float *cptr[9] = {s.w[0], s.w[1], s.w[2], s.w[3], nullptr, nullptr, nullptr, nullptr, nullptr};
+#pragma unroll
+    for (int q = 0; q < NUNK; q++) { cptr[CI_C + q] = s.c[q]; cptr[CI_D + q] = s.d[q]; }
+    if (NUNK == 2) cptr[CI_M] = s.m;
+    const int ti = (tid & 31) * 4, tj = tid >> 5;
+    const int gi0 = i0 + ti, gj = j0 + tj;
+    const bool row_ok = gj < nc && gi0 < nr;
+    // ---- all copies, nothing held in registers ----
+    {
+        const long long p = base + (long long)min(gj, nc - 1) * nr + min(gi0, nr - 4);   // nr is a multiple of 4
+#pragma unroll
+        for (int f = 0; f < NC; f++) cp_async16(&cf[f][tj][ti], cptr[f] + p);
+    }
+    int rli = -1, rlj = 0;                                    // the red pixels of the 1-pixel ring (see rb_tile_kernel)
+    if (tid < 65) { rli = 2 * tid; rlj = 0; }
+    else if (tid < 130) { rli = 2 * (tid - 65) + 1; rlj = PT_J + 1; }
+    else if (tid < 134) { rli = 0; rlj = 2 * (tid - 130) + 2; }
+    else if (tid < 138) { rli = PT_I + 1; rlj = 2 * (tid - 134) + 1; }
+    bool ring_ok = false;
+    if (rli >= 0) {
+        const int gi = i0 + rli - 1, gjr = j0 + rlj - 1;
+        ring_ok = gi >= 1 && gi <= nr - 2 && gjr >= 1 && gjr <= nc - 2;
+        const long long p = base + (long long)min(max(gjr, 0), nc - 1) * nr + min(max(gi, 0), nr - 1);
+#pragma unroll
+        for (int f = 0; f < NC; f++) cp_async4(&rg[f * PT_RING + tid], cptr[f] + p);
+    }
+    for (int t = tid; t < (PT_I / 4) * PS_J; t += 256) {
+        const int v = t % (PT_I / 4), lj = t / (PT_I / 4);
+        const int gjc = min(max(j0 + lj - PT_H, 0), nc - 1);
+        const long long p = (long long)gjc * nr + min(i0 + 4 * v, nr - 4);
+#pragma unroll
+        for (int f = 0; f < NF; f++) cp_async16(&sm[f][lj][PT_C0 + 4 * v], field(f) + p);
+    }
+    for (int t = tid; t < 2 * PT_H * PS_J; t += 256) {
+        const int h = t % (2 * PT_H), lj = t / (2 * PT_H);
+        const int c = h < PT_H ? PT_C0 - PT_H + h : PT_C0 + PT_I + h - PT_H;       // columns 2,3 and 132,133
+        const int gi = min(max(i0 + c - PT_C0, 0), nr - 1), gjc = min(max(j0 + lj - PT_H, 0), nc - 1);
+        const long long p = (long long)gjc * nr + gi;
+#pragma unroll
+        for (int f = 0; f < NF; f++) cp_async4(&sm[f][lj][c], field(f) + p);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    auto update = [&](int c, int lj) {                        // scalar update of a ring pixel
+        float xn[2][4], xc[2], x0n[2][4], x0c[2], out[2], w[4], C[2] = {0.f, 0.f}, D[2] = {0.f, 0.f};
+#pragma unroll
+        for (int n = 0; n < 4; n++) w[n] = rg[n * PT_RING + tid];
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            C[q] = rg[(CI_C + q) * PT_RING + tid]; D[q] = rg[(CI_D + q) * PT_RING + tid];
+            xc[q] = sm[q][lj][c];
+            xn[q][W_W] = sm[q][lj - 1][c]; xn[q][W_E] = sm[q][lj + 1][c];
+            xn[q][W_N] = sm[q][lj][c - 1]; xn[q][W_S] = sm[q][lj][c + 1];
+            if (F::LATE) {
+                x0c[q] = sm[NUNK + q][lj][c];
+                x0n[q][W_W] = sm[NUNK + q][lj - 1][c]; x0n[q][W_E] = sm[NUNK + q][lj + 1][c];
+                x0n[q][W_N] = sm[NUNK + q][lj][c - 1]; x0n[q][W_S] = sm[NUNK + q][lj][c + 1];
+            }
+        }
+        point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, NUNK == 2 ? rg[CI_M * PT_RING + tid] : 0.f, omega, out);
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) sm[q][lj][c] = out[q];
+    };
+    float4 xk[2];
+    auto own = [&](int colour) {
+        const int lj = tj + PT_H, c = PT_C0 + ti;
+        float4 vc[NF], vw[NF], ve[NF];
+        float lf[NF], rt[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++) {
+            vc[f] = *reinterpret_cast<const float4 *>(&sm[f][lj][c]);
+            vw[f] = *reinterpret_cast<const float4 *>(&sm[f][lj - 1][c]);
+            ve[f] = *reinterpret_cast<const float4 *>(&sm[f][lj + 1][c]);
+            lf[f] = sm[f][lj][c - 1]; rt[f] = sm[f][lj][c + 4];
+        }
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) xk[q] = vc[q];
+        if (!row_ok || gj < 1 || gj > nc - 2) return;
+        float4 k4[NC];
+#pragma unroll
+        for (int f = 0; f < NC; f++) k4[f] = *reinterpret_cast<const float4 *>(&cf[f][tj][ti]);
+        float res[2][4];
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) { res[q][0] = vc[q].x; res[q][1] = vc[q].y; res[q][2] = vc[q].z; res[q][3] = vc[q].w; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gi = gi0 + k;
+            if (gi < 1 || gi > nr - 2 || ((gi + gj) & 1) != colour) continue;
+            float xn[2][4], xc[2], x0n[2][4], x0c[2], out[2];
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) {
+                xc[q] = f4c(vc[q], k);
+                xn[q][W_W] = f4c(vw[q], k); xn[q][W_E] = f4c(ve[q], k);
+                xn[q][W_N] = k > 0 ? f4c(vc[q], k - 1) : lf[q];
+                xn[q][W_S] = k < 3 ? f4c(vc[q], k + 1) : rt[q];
+                if (F::LATE) {
+                    x0c[q] = f4c(vc[NUNK + q], k);
+                    x0n[q][W_W] = f4c(vw[NUNK + q], k); x0n[q][W_E] = f4c(ve[NUNK + q], k);
+                    x0n[q][W_N] = k > 0 ? f4c(vc[NUNK + q], k - 1) : lf[NUNK + q];
+                    x0n[q][W_S] = k < 3 ? f4c(vc[NUNK + q], k + 1) : rt[NUNK + q];
+                }
+            }
+            const float w[4] = {f4c(k4[0], k), f4c(k4[1], k), f4c(k4[2], k), f4c(k4[3], k)};
+            const float C[2] = {f4c(k4[CI_C], k), NUNK == 2 ? f4c(k4[CI_C + NUNK - 1], k) : 0.f};
+            const float D[2] = {f4c(k4[CI_D], k), NUNK == 2 ? f4c(k4[CI_D + NUNK - 1], k) : 0.f};
+            point_formula<FAM>(w, xn, xc, x0n, x0c, C, D, NUNK == 2 ? f4c(k4[NC - 1], k) : 0.f, omega, out);
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) res[q][k] = out[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            xk[q] = make_float4(res[q][0], res[q][1], res[q][2], res[q][3]);
+            *reinterpret_cast<float4 *>(&sm[q][lj][c]) = xk[q];
+        }
+    };
+    own(0);
+    if (ring_ok) update(rli + PT_C0 - 1, rlj + PT_H - 1);
+    __syncthreads();
+    own(1);
+    if (row_ok) {
+        float *xo[2] = {xo0 + base, NUNK == 2 ? xo1 + base : nullptr};
+        const long long p = (long long)gj * nr + gi0;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) *reinterpret_cast<float4 *>(xo[q] + p) = xk[q];
+    }
+}
+
 template <int NUNK>
 __global__ void border_fill_tile_kernel(float *x0, float *x1, int nr, int nc, long long bstride)
 {
@@ -236,6 +415,15 @@ int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     for (int n = 0; n < 4; n++) al = al && a16(sys->w[n]);
     for (int q = 0; q < NUNK; q++) al = al && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]);
     if (NUNK == 2) al = al && a16(sys->m);
+    static const int use_async = getenv("PDEGPU_POINT_ASYNC") ? atoi(getenv("PDEGPU_POINT_ASYNC")) : 1;
+    if (al && use_async) {
+        static bool attr_set[16] = {false};
+        if (!attr_set[ctx->device & 15]) {
+            cudaError_t e = cudaFuncSetAttribute(rb_tile_async_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pt_async_floats<FAM>() * sizeof(float)));
+            if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(rb_tile_async_kernel)");
+            attr_set[ctx->device & 15] = true;
+        }
+    }
     SysView v = make_view(sys);
     dim3 grid((sys->nrows + PT_I - 1) / PT_I, (sys->ncols + PT_J - 1) / PT_J, sys->batch);
     const int per = 2 * sys->nrows + 2 * sys->ncols;
@@ -244,7 +432,8 @@ int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     for (int it = 0; it < iter; it++) {
         v.x[0] = cur[0]; v.x[1] = cur[1];
         PDEGPU_PROF(ctx, "rb_tile_kernel", sweep_bytes<FAM>() * (double)npix * sys->batch);
-        if (al) rb_tile_kernel<FAM, true><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega);
+        if (al && use_async) rb_tile_async_kernel<FAM><<<grid, 256, pt_async_floats<FAM>() * sizeof(float), ctx->stream>>>(v, nxt[0], nxt[1], omega);
+        else if (al) rb_tile_kernel<FAM, true><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega);
         else rb_tile_kernel<FAM, false><<<grid, 256, 0, ctx->stream>>>(v, nxt[0], nxt[1], omega);
         PDEGPU_LAUNCH_CHECK(ctx, "rb_tile_kernel");
         PDEGPU_PROF(ctx, "border_fill_kernel", 0);
