@@ -61,6 +61,89 @@ extern "C" int pdegpu_init(int device, pdegpu_ctx **out)
     return PDEGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// CUDA graphs of whole pipelines
+// ---------------------------------------------------------------------------------------------
+constexpr int kGraphSlots = 8, kGraphKeyMax = 256;
+struct pdegpu_graph_entry {
+    unsigned char key[kGraphKeyMax];
+    size_t key_len;
+    unsigned epoch;
+    int state;                       // 0 empty, 1 seen once (ran directly), 2 graph ready, 3 capture failed: always direct
+    cudaGraphExec_t exec;
+    unsigned long long launches;     // launches one replay stands for
+    unsigned long long last_use;
+};
+
+static void pdegpu_graphs_drop(pdegpu_ctx *ctx)
+{
+    if (!ctx->graphs) return;
+    for (int k = 0; k < kGraphSlots; k++) {
+        if (ctx->graphs[k].state == 2 && ctx->graphs[k].exec) cudaGraphExecDestroy(ctx->graphs[k].exec);
+        ctx->graphs[k].state = 0; ctx->graphs[k].exec = nullptr;
+    }
+}
+
+int pdegpu_graph_run(pdegpu_ctx *ctx, const void *key, size_t key_len, pdegpu_graph_body body)
+{
+    static const int enabled = getenv("PDEGPU_GRAPHS") ? atoi(getenv("PDEGPU_GRAPHS")) : 1;
+    static unsigned long long tick = 0;
+    if (!enabled || ctx->prof_on || ctx->capturing || key_len > (size_t)kGraphKeyMax) return body.fn(body.arg);
+    if (!ctx->graphs) {
+        ctx->graphs = (pdegpu_graph_entry *)calloc(kGraphSlots, sizeof(pdegpu_graph_entry));
+        if (!ctx->graphs) return body.fn(body.arg);
+    }
+    pdegpu_graph_entry *e = nullptr, *victim = nullptr;
+    for (int k = 0; k < kGraphSlots; k++) {
+        pdegpu_graph_entry &g = ctx->graphs[k];
+        if (g.state && g.epoch != ctx->graph_epoch) {                         // its device pointers are gone
+            if (g.state == 2 && g.exec) cudaGraphExecDestroy(g.exec);
+            g.state = 0; g.exec = nullptr;
+        }
+        if (g.state && g.key_len == key_len && memcmp(g.key, key, key_len) == 0) e = &g;
+        // replacement: an empty slot if there is one, else the least recently used
+        if (!victim || (victim->state != 0 && (g.state == 0 || g.last_use < victim->last_use))) victim = &g;
+    }
+    if (!e) {                                                                 // first sight of this call: run it as it is
+        if (victim->state == 2 && victim->exec) cudaGraphExecDestroy(victim->exec);
+        memset(victim, 0, sizeof *victim);
+        memcpy(victim->key, key, key_len);
+        victim->key_len = key_len; victim->state = 1; victim->last_use = ++tick;
+        const int rc = body.fn(body.arg);
+        victim->epoch = ctx->graph_epoch;                                     // after the run: the run itself may have grown a buffer
+        return rc;
+    }
+    e->last_use = ++tick;
+    if (e->state == 3) return body.fn(body.arg);
+    if (e->state == 1) {                                                      // second call: capture
+        const unsigned long long l0 = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError(); e->state = 3; return body.fn(body.arg);
+        }
+        ctx->capturing = 1;
+        const int rc = body.fn(body.arg);
+        ctx->capturing = 0;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != PDEGPU_OK || ce != cudaSuccess || !graph || e->epoch != ctx->graph_epoch) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            e->state = 3; e->epoch = ctx->graph_epoch;
+            ctx->launches = l0;
+            return body.fn(body.arg);                                         // nothing ran during the capture
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess || !exec) { cudaGetLastError(); e->state = 3; ctx->launches = l0; return body.fn(body.arg); }
+        e->exec = exec; e->state = 2; e->launches = ctx->launches - l0;
+        ctx->launches = l0;
+    }
+    ctx->launches += e->launches;
+    PDEGPU_CUDA_OK(ctx, cudaGraphLaunch(e->exec, ctx->stream));
+    return PDEGPU_OK;
+}
+
 extern "C" void pdegpu_free(pdegpu_ctx *ctx)
 {
     if (!ctx) return;
@@ -70,6 +153,8 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
         for (int k = 0; k < ctx->prof_cap; k++) if (ctx->prof[k].e0) { cudaEventDestroy(ctx->prof[k].e0); cudaEventDestroy(ctx->prof[k].e1); }
         free(ctx->prof);
     }
+    pdegpu_graphs_drop(ctx);
+    free(ctx->graphs);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work) cudaFree(ctx->work);
@@ -162,6 +247,7 @@ int pdegpu_arena_reserve(pdegpu_ctx *ctx, size_t bytes)
     if (ctx->arena_used != 0) return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "arena grow while in use");
     PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->arena) { cudaFree(ctx->arena); ctx->arena = nullptr; ctx->arena_bytes = 0; }
+    ctx->graph_epoch++;
     size_t want = bytes + (bytes >> 3) + (1u << 20);
     cudaError_t e = cudaMalloc((void **)&ctx->arena, want);
     if (e != cudaSuccess) {
@@ -189,6 +275,7 @@ int pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes)
     if (bytes <= ctx->scratch_bytes) return PDEGPU_OK;
     PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+    ctx->graph_epoch++;
     size_t want = bytes + (bytes >> 3) + (1u << 20);
     cudaError_t e = cudaMalloc((void **)&ctx->scratch, want);
     if (e != cudaSuccess) {
@@ -198,6 +285,22 @@ int pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes)
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaMalloc(scratch)");
     }
     ctx->scratch_bytes = want;
+    return PDEGPU_OK;
+}
+
+// workspace of the device-resident pipelines
+int pdegpu_work_reserve(pdegpu_ctx *ctx, size_t bytes, const char *who)
+{
+    if (bytes <= ctx->work_bytes) return PDEGPU_OK;
+    PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->work) cudaFree(ctx->work);
+    ctx->work = nullptr; ctx->work_bytes = 0;
+    ctx->graph_epoch++;
+    if (cudaMalloc((void **)&ctx->work, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "%s: cannot allocate %zu bytes of workspace", who, bytes);
+    }
+    ctx->work_bytes = bytes;
     return PDEGPU_OK;
 }
 

@@ -32,8 +32,20 @@ struct pdegpu_ctx {
     // workspace of the device-resident pipelines (pipeline.cu), grown on demand
     char         *work;
     size_t        work_bytes;
+    // CUDA graphs of whole driver pipelines (pdegpu_graph_run): device pointers are baked in, so every reallocation of
+    // arena / scratch / work bumps the epoch and the cached graphs die
+    unsigned      graph_epoch;
+    int           capturing;
+    struct pdegpu_graph_entry *graphs;
     char          err[512];
 };
+
+// Runs `body` (a sequence of launches on ctx->stream with no host synchronisation) and, from the second call with the
+// same `key` on, replays it as a CUDA graph: the pipelines issue thousands of small dependent launches per call (4400
+// per 1080p FMG pair), whose launch latency a graph removes. Falls back to running `body` directly when profiling is
+// on, when PDEGPU_GRAPHS=0, or when the capture fails. `key` must cover every argument the launches depend on.
+struct pdegpu_graph_body { int (*fn)(void *); void *arg; };
+int pdegpu_graph_run(pdegpu_ctx *ctx, const void *key, size_t key_len, pdegpu_graph_body body);
 
 struct pdegpu_prof_rec {
     const char  *name;
@@ -51,6 +63,7 @@ int  pdegpu_arena_reserve(pdegpu_ctx *ctx, size_t bytes);     // make sure capac
 void pdegpu_arena_reset(pdegpu_ctx *ctx);
 void *pdegpu_arena_alloc(pdegpu_ctx *ctx, size_t bytes);      // nullptr if exhausted
 int  pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes);   // ctx->scratch valid for >= bytes afterwards
+int  pdegpu_work_reserve(pdegpu_ctx *ctx, size_t bytes, const char *who);   // ctx->work valid for >= bytes afterwards
 
 #define PDEGPU_CUDA_OK(ctx, call)                                                 \
     do {                                                                          \

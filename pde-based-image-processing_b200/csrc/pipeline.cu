@@ -205,15 +205,18 @@ extern "C" int pdegpu_dev_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, cons
     Bump b = {nullptr, 0, 0, true};
     int rc = flow_llin_run(ctx, b, U, V, I0, I1, nrows, ncols, channels, batch, *params);
     if (rc) return rc;
-    if (b.used > ctx->work_bytes) {
-        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->work) cudaFree(ctx->work);
-        ctx->work = nullptr; ctx->work_bytes = 0;
-        if (cudaMalloc((void **)&ctx->work, b.used) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_flow_llin_2d: cannot allocate %zu bytes of workspace", b.used); }
-        ctx->work_bytes = b.used;
-    }
-    Bump w = {ctx->work, ctx->work_bytes, 0, false};
-    return flow_llin_run(ctx, w, U, V, I0, I1, nrows, ncols, channels, batch, *params);
+    if ((rc = pdegpu_work_reserve(ctx, b.used, "pdegpu_dev_flow_llin_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_llin_params P; char *work; size_t wb; int id; };
+    Args a;
+    memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
+    a.ctx = ctx; a.U = U; a.V = V; a.I0 = I0; a.I1 = I1; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
+    a.P = *params; a.work = ctx->work; a.wb = ctx->work_bytes; a.id = 1;
+    pdegpu_graph_body body = {[](void *p) -> int {
+        Args &a = *static_cast<Args *>(p);
+        Bump w = {a.work, a.wb, 0, false};
+        return flow_llin_run(a.ctx, w, a.U, a.V, a.I0, a.I1, a.nrows, a.ncols, a.channels, a.batch, a.P);
+    }, &a};
+    return pdegpu_graph_run(ctx, &a, sizeof a, body);
 }
 
 extern "C" int pdegpu_flow_llin_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
@@ -303,13 +306,7 @@ extern "C" int pdegpu_dev_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *
     Bump b = {nullptr, 0, 0, true};
     int rc = tv_run(ctx, b, Iout, Iin, nrows, ncols, nframes, *params);
     if (rc) return rc;
-    if (b.used > ctx->work_bytes) {
-        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->work) cudaFree(ctx->work);
-        ctx->work = nullptr; ctx->work_bytes = 0;
-        if (cudaMalloc((void **)&ctx->work, b.used) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_tvdenoise8: cannot allocate %zu bytes of workspace", b.used); }
-        ctx->work_bytes = b.used;
-    }
+    if ((rc = pdegpu_work_reserve(ctx, b.used, "pdegpu_dev_tvdenoise8"))) return rc;
     Bump w = {ctx->work, ctx->work_bytes, 0, false};
     return tv_run(ctx, w, Iout, Iin, nrows, ncols, nframes, *params);
 }

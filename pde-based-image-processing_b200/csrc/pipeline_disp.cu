@@ -172,20 +172,23 @@ extern "C" int pdegpu_dev_disp_sym_2d(pdegpu_ctx *ctx, float *U, const float *Il
     Bump2 dry = {nullptr, 0, true};
     int rc = disp_run(ctx, dry, U, Il, Ir, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if (dry.used > ctx->work_bytes) {
-        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->work) cudaFree(ctx->work);
-        ctx->work = nullptr; ctx->work_bytes = 0;
-        if (cudaMalloc((void **)&ctx->work, dry.used) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_disp_sym_2d: cannot allocate %zu bytes of workspace", dry.used); }
-        ctx->work_bytes = dry.used;
-    }
-    const size_t np = (size_t)nrows * ncols;
-    for (int bi = 0; bi < batch; bi++) {
-        Bump2 w = {ctx->work, 0, false};
-        rc = disp_run(ctx, w, U + 2 * bi * np, Il + bi * np * channels, Ir + bi * np * channels, nrows, ncols, channels, *params);
-        if (rc) return rc;
-    }
-    return PDEGPU_OK;
+    if ((rc = pdegpu_work_reserve(ctx, dry.used, "pdegpu_dev_disp_sym_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U; const float *Il, *Ir; int nrows, ncols, channels, batch; pdegpu_disp_sym_params P; char *work; int id; };
+    Args a;
+    memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
+    a.ctx = ctx; a.U = U; a.Il = Il; a.Ir = Ir; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
+    a.P = *params; a.work = ctx->work; a.id = 4;
+    pdegpu_graph_body body = {[](void *p) -> int {
+        Args &a = *static_cast<Args *>(p);
+        const size_t np = (size_t)a.nrows * a.ncols;
+        for (int bi = 0; bi < a.batch; bi++) {
+            Bump2 w = {a.work, 0, false};
+            const int rc = disp_run(a.ctx, w, a.U + 2 * bi * np, a.Il + bi * np * a.channels, a.Ir + bi * np * a.channels, a.nrows, a.ncols, a.channels, a.P);
+            if (rc) return rc;
+        }
+        return PDEGPU_OK;
+    }, &a};
+    return pdegpu_graph_run(ctx, &a, sizeof a, body);
 }
 
 extern "C" int pdegpu_disp_sym_2d(pdegpu_ctx *ctx, float *U, const float *Il, const float *Ir,

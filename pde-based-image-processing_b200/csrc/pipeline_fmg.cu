@@ -291,20 +291,24 @@ extern "C" int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const
     Stack dry = {nullptr, 0, 0, true};
     int rc = fmg_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if (dry.peak > ctx->work_bytes) {
-        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->work) cudaFree(ctx->work);
-        ctx->work = nullptr; ctx->work_bytes = 0;
-        if (cudaMalloc((void **)&ctx->work, dry.peak) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_flow_fmg_2d: cannot allocate %zu bytes of workspace", dry.peak); }
-        ctx->work_bytes = dry.peak;
-    }
-    const size_t np = (size_t)nrows * ncols;
-    for (int bi = 0; bi < batch; bi++) {
-        Stack w = {ctx->work, 0, 0, false};
-        rc = fmg_run(ctx, w, U + bi * np, V + bi * np, I0 + bi * np * channels, I1 + bi * np * channels, nrows, ncols, channels, *params);
-        if (rc) return rc;
-    }
-    return PDEGPU_OK;
+    if ((rc = pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_fmg_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_fmg_params P; char *work; int id; };
+    Args a;
+    memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
+    a.ctx = ctx; a.U = U; a.V = V; a.I0 = I0; a.I1 = I1; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
+    a.P = *params; a.work = ctx->work; a.id = 2;
+    pdegpu_graph_body body = {[](void *p) -> int {
+        Args &a = *static_cast<Args *>(p);
+        const size_t np = (size_t)a.nrows * a.ncols;
+        for (int bi = 0; bi < a.batch; bi++) {
+            Stack w = {a.work, 0, 0, false};
+            const int rc = fmg_run(a.ctx, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
+                                   a.nrows, a.ncols, a.channels, a.P);
+            if (rc) return rc;
+        }
+        return PDEGPU_OK;
+    }, &a};
+    return pdegpu_graph_run(ctx, &a, sizeof a, body);
 }
 
 extern "C" int pdegpu_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,
@@ -439,20 +443,24 @@ extern "C" int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const 
     Stack dry = {nullptr, 0, 0, true};
     int rc = hs_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if (dry.peak > ctx->work_bytes) {
-        PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->work) cudaFree(ctx->work);
-        ctx->work = nullptr; ctx->work_bytes = 0;
-        if (cudaMalloc((void **)&ctx->work, dry.peak) != cudaSuccess) { cudaGetLastError(); return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "pdegpu_dev_flow_hs_2d: cannot allocate %zu bytes of workspace", dry.peak); }
-        ctx->work_bytes = dry.peak;
-    }
-    const size_t np = (size_t)nrows * ncols;
-    for (int bi = 0; bi < batch; bi++) {
-        Stack w = {ctx->work, 0, 0, false};
-        rc = hs_run(ctx, w, U + bi * np, V + bi * np, I0 + bi * np * channels, I1 + bi * np * channels, nrows, ncols, channels, *params);
-        if (rc) return rc;
-    }
-    return PDEGPU_OK;
+    if ((rc = pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_hs_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_hs_params P; char *work; int id; };
+    Args a;
+    memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
+    a.ctx = ctx; a.U = U; a.V = V; a.I0 = I0; a.I1 = I1; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
+    a.P = *params; a.work = ctx->work; a.id = 3;
+    pdegpu_graph_body body = {[](void *p) -> int {
+        Args &a = *static_cast<Args *>(p);
+        const size_t np = (size_t)a.nrows * a.ncols;
+        for (int bi = 0; bi < a.batch; bi++) {
+            Stack w = {a.work, 0, 0, false};
+            const int rc = hs_run(a.ctx, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
+                                   a.nrows, a.ncols, a.channels, a.P);
+            if (rc) return rc;
+        }
+        return PDEGPU_OK;
+    }, &a};
+    return pdegpu_graph_run(ctx, &a, sizeof a, body);
 }
 
 extern "C" int pdegpu_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const float *I0, const float *I1,

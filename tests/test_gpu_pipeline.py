@@ -212,3 +212,32 @@ def test_disp_sym_default_parameters_quality(ctx):
     assert abs(eg - eo) < 0.02 and eg < 0.2, f"mean abs disparity error: GPU {eg}, reference {eo}"
     # symmetry: the right -> left field mirrors the left -> right one
     assert float(np.nanmean(np.abs(g1[s] + u[s]))) < 0.2
+
+
+# ---- CUDA-graph replay of the pipelines (pdegpu_graph_run): call 1 runs the launches directly, call 2 captures them,
+#      call 3 replays the graph; all three must return the same bits, and a different input must not hit a stale graph ----
+def test_pipeline_graph_replay_is_bitwise(built):
+    from pdegpu import lib
+    c = lib.Context(0)
+    nr, nc = 64, 80
+    I0, I1, _, _ = small_pair(51, nr, nc, 1)
+    J0, J1, _, _ = small_pair(52, nr, nc, 1)
+    l0 = c.launches
+    a = c.flow_fmg(I0, I1)
+    per_call = c.launches - l0
+    b = c.flow_fmg(I0, I1)
+    d = c.flow_fmg(I0, I1)
+    assert c.launches - l0 == 3 * per_call                       # replays are counted like the launches they stand for
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[0], d[0]) and np.array_equal(a[1], d[1])
+    e = c.flow_fmg(J0, J1)                                       # same buffers, new content: the graph reads the new data
+    assert not np.array_equal(e[0], a[0])
+    f = c.flow_fmg(J0, J1, iter=8)                               # other parameters: another key
+    assert not np.array_equal(f[0], e[0])
+    P0, P1, _, _ = pair(53, nr, nc)
+    r = [c.flow_llin(P0, P1) for _ in range(3)]
+    assert np.array_equal(r[0][0], r[1][0]) and np.array_equal(r[0][0], r[2][0])
+    Sl, Sr, _ = stereo_pair(54, nr, nc, 1)
+    q = [c.disp_sym(Sl, Sr) for _ in range(3)]
+    assert np.array_equal(q[0][0], q[2][0], equal_nan=True) and np.array_equal(q[0][1], q[2][1], equal_nan=True)
+    h = [c.flow_hs(P0, P1) for _ in range(3)]
+    assert np.array_equal(h[0][0], h[2][0])

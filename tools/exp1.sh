@@ -1,8 +1,5 @@
 #!/bin/bash
 cd /root/repo
-timeout 300 python -m pytest tests/test_gpu_sweeps.py -x -q -m gpu < /dev/null 2>&1 | tail -3
-P="timeout 120 python tools/w2_probe.py 64"
-D=pde-based-image-processing_b200
-echo "== point async (3 CTAs/SM)"; W2_SOLVER=1 $P < /dev/null 2>&1 | grep rb_tile
-echo "== point async (2 CTAs/SM, no spills)"; W2_SOLVER=1 PDEGPU_LIB=$D/libpdegpu_pta2.so $P < /dev/null 2>&1 | grep rb_tile
-echo "== point register-staged"; W2_SOLVER=1 PDEGPU_POINT_ASYNC=0 $P < /dev/null 2>&1 | grep rb_tile
+timeout 400 python -m pytest tests/test_gpu_pipeline.py -x -q -m gpu < /dev/null 2>&1 | tail -6
+timeout 400 python bench.py --steps 5 --warmup 3 < /dev/null > gpurun_out/bench_e1.json 2> gpurun_out/bench_e1.err; echo "bench rc $?"
+PDEGPU_GRAPHS=0 timeout 400 python bench.py --steps 5 --warmup 3 < /dev/null > gpurun_out/bench_e1_nograph.json 2> gpurun_out/bench_e1_nograph.err; echo "bench nograph rc $?"
