@@ -582,6 +582,16 @@ def run_ours(args):
                     "launch_ms_avg": top["ms_total"] / top["launches"], "launches": top["launches"],
                     "share_of_step": top["ms_total"] / total_kernel_ms,
                     "algorithmic_bytes_per_launch": top["bytes_total"] / top["launches"]}
+        if roof:
+            # measured DRAM traffic of that kernel from the committed ncu capture (same workload only)
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    tr = json.load(f)
+                if (tr["batch_per_gpu"], tr["nrows"], tr["ncols"]) == (B, NROWS, NCOLS):
+                    roof["traffic"] = tr["bytes_per_launch"].get(top["kernel"])
+                    roof["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram read + write bytes per launch)"
+            except (OSError, KeyError, ValueError):
+                pass
         cpu, _ = cpu_reference_throughput(seconds_target=10.0) if world == 1 else (None, 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
