@@ -1,0 +1,59 @@
+"""BASELINE.json's full sizes, where the CPU checker cannot follow in seconds: the driver pipelines are checked through
+properties that do not need it -- a known synthetic displacement is recovered, denoising moves towards the clean image,
+outputs are finite, a second call returns the same bits."""
+import numpy as np
+import pytest
+
+from pdegpu import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    from pdegpu import lib
+    return lib.Context(0)
+
+
+def test_fmg_1080p_recovers_subpixel_flow(ctx):
+    """configs[2]: early-linearisation FMG flow on a 1920x1080 pair"""
+    nr, nc = 1080, 1920
+    I0, I1, u, v = synth.image_pair(300, nr, nc, nframes=1, scale=255.0, max_flow=0.8)
+    # driver defaults. One FMG pass with 4 outer iterations per level is far from converged at this size on either side:
+    # measured AEE 0.167 px here against 0.127 px for the restatement on the reference MEX code (bench.py, `fmg` leg),
+    # for a mean displacement of 0.26 px; the property checked is that the flow is finite and clearly better than none
+    U, V = ctx.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1))
+    assert np.isfinite(U).all() and np.isfinite(V).all()
+    s = (slice(8, -8), slice(8, -8))
+    aee = float(np.mean(np.sqrt((U[s] - u[s]) ** 2 + (V[s] - v[s]) ** 2)))
+    mag = float(np.mean(np.sqrt(u ** 2 + v ** 2)))
+    assert aee < 0.8 * mag, f"AEE {aee} for a mean displacement of {mag}"
+
+
+def test_symmetric_stereo_4096x2160(ctx):
+    """configs[3], stereo half: horizontal shift of up to 8 px on a 4096x2160 pair"""
+    nr, nc = 2160, 4096
+    Il, Ir, u, _ = synth.image_pair(301, nr, nc, nframes=1, scale=255.0, max_flow=8.0 / 0.55, horizontal=True)
+    assert float(np.abs(u).max()) <= 8.01
+    U0, U1 = ctx.disp_sym(Il, Ir)
+    s = (slice(16, -16), slice(16, -16))
+    ok = np.isfinite(U0[s]) & np.isfinite(U1[s])
+    assert ok.mean() > 0.99
+    e0 = float(np.nanmean(np.abs(U0[s] - u[s]))); e1 = float(np.nanmean(np.abs(U1[s] + u[s])))
+    mag = float(np.mean(np.abs(u)))
+    assert e0 < 0.25 * mag and e1 < 0.25 * mag, f"mean abs disparity error {e0} / {e1} for a mean disparity of {mag}"
+    V0, V1 = ctx.disp_sym(Il, Ir)
+    assert np.array_equal(U0, V0, equal_nan=True) and np.array_equal(U1, V1, equal_nan=True)
+
+
+def test_tvdenoise8_4096x2160(ctx):
+    """configs[3], denoising half: 8-neighbour anisotropic TV on a 4096x2160 image"""
+    nr, nc = 2160, 4096
+    rng = np.random.default_rng(302)
+    ii, jj = np.meshgrid(np.arange(nr), np.arange(nc), indexing="ij")
+    clean = (0.5 + 0.3 * np.sign(np.sin(ii / 90.0) * np.cos(jj / 110.0))).astype(np.float32)
+    noisy = (clean + 0.08 * rng.standard_normal(clean.shape)).astype(np.float32)
+    out = ctx.tvdenoise8(noisy, outer_iter=5)
+    assert out.shape == noisy.shape and np.isfinite(out).all()
+    rm = lambda a: float(np.sqrt(np.mean((a - clean) ** 2)))
+    assert rm(out) < 0.8 * rm(noisy), f"RMSE vs clean: {rm(out)} after, {rm(noisy)} before"
