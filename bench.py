@@ -209,7 +209,21 @@ def run_reference(args):
 # flows/s leg: the whole configs[1] driver (FlowEminND_llin_2D_v10: 13-level pyramid, 4x4 fixed-point
 # loops, ALR iter=4) on a batch of synthetic 640x480 RGB pairs, device resident and end to end
 # ---------------------------------------------------------------------------------------------
-def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
+def timed_median(fn, reps, stream, barrier):
+    """median over `reps` calls of fn, each timed with its own CUDA event pair on the library's stream (ms)"""
+    import torch
+    ts = []
+    for _ in range(reps):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        fn()
+        ev1.record(stream)
+        barrier()
+        ts.append(ev0.elapsed_time(ev1))
+    return float(np.median(ts))
+
+
+def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
     import torch
     from pdegpu import lib, synth
     C = 3
@@ -244,16 +258,13 @@ def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    dev_run(); host_run()
+    for _ in range(3):                 # direct run, graph capture, first replay (pdegpu_graph_run) -- none of them timed
+        dev_run()
+    for _ in range(3):
+        host_run()
     barrier()
     l0 = ctx.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(reps):
-        dev_run()
-    ev1.record(stream)
-    barrier()
-    ms = maxr(ev0.elapsed_time(ev1)) / reps
+    ms = maxr(timed_median(dev_run, reps, stream, barrier))
     launches = (ctx.launches - l0) // reps
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -286,7 +297,7 @@ def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
 # FMG leg: BASELINE configs[2], the whole FlowEminNDFASFMG_elin_2D_v10 driver (early linearisation, full multigrid,
 # one FAS V-cycle per level, firstLoop=4, ALR iter=4) on synthetic 1920x1080 pairs, device resident and end to end
 # ---------------------------------------------------------------------------------------------
-def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
+def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
     import torch
     from pdegpu import lib, synth
     NR, NC, C = 1080, 1920, 1                      # runme.m:90 runs this driver on single-channel frames
@@ -328,21 +339,17 @@ def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
         return float(np.mean(np.sqrt((Ua[sl] - u[sl]) ** 2 + (Va[sl] - v[sl]) ** 2)))
 
     def timed(pp):
-        dev_run(pp)
+        for _ in range(3):             # direct run, graph capture, first replay -- none of them timed
+            dev_run(pp)
         barrier()
         l0 = ctx.launches
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(reps):
-            dev_run(pp)
-        ev1.record(stream)
-        barrier()
-        ms = maxr(ev0.elapsed_time(ev1)) / reps
+        ms = maxr(timed_median(lambda: dev_run(pp), reps, stream, barrier))
         Ug = U[0].cpu().numpy().reshape(NR, NC, order="F"); Vg = V[0].cpu().numpy().reshape(NR, NC, order="F")
         return ms, (ctx.launches - l0) // reps, aee_of(Ug, Vg)
 
     ms, launches, aee = timed(p)
-    host_run()
+    for _ in range(3):
+        host_run()
     barrier()
     t0 = time.perf_counter()
     for _ in range(reps):

@@ -85,7 +85,7 @@ alr_window_kernel(const WinParams p)
         return true;
     };
     const int ec_last = (n - 1) & ~3;                        // first element of the last (possibly partial) vector of a line
-    const bool al = p.aligned != 0;
+    const bool al = p.aligned == 2;
     auto first_element = [&](int t, int &e0, int &ec) { e0 = 128 * t + 4 * lane; ec = min(e0, ec_last); };
 
     RawBatch<FAM> raw[2];
@@ -200,7 +200,7 @@ alr_window_kernel(const WinParams p)
             for (int qq = 0; qq < NUNK; qq++) {
                 float *o = p.xout[qq] + (long long)cur.img * p.ostride + j0;
                 const float *rq = rblk + qq * P;
-                if (cnt == 8 && p.vec_ok) {
+                if (cnt == 8 && p.vec_ok == 2) {
                     // half-warp h writes lines 4h..4h+3 of 16 consecutive elements: full 32-B sectors
                     const int h = lane >> 4;
                     const float *rh = rq + (size_t)(4 * h) * SP;
@@ -287,17 +287,24 @@ int window_pass(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const xout[2],
     p.R = g.R; p.D = g.D;
     p.omega = omega;
     p.G = 1;
-    bool al = (sys->ncols % 4 == 0) && (ostride % 4 == 0);
-    for (int q = 0; q < F::NUNK; q++) al = al && ((uintptr_t)xout[q] % 16 == 0);
-    p.vec_ok = al ? 1 : 0;
-    {   // float4 loads need every field 16-B aligned, lines and problems a multiple of 4 floats long
+    auto oal = [&](int vw) {                                 // X_out stores: 2 = 16-byte, 1 = 8-byte (two-stage kernel), 0 = scalar
+        bool a = (sys->ncols % vw == 0) && (ostride % vw == 0);
+        for (int q = 0; q < F::NUNK; q++) a = a && ((uintptr_t)xout[q] % (4 * vw) == 0);
+        return a;
+    };
+    p.vec_ok = oal(4) ? 2 : oal(2) ? 1 : 0;
+    {   // vector loads: 16-byte ones need every field 16-B aligned and lines / problems a multiple of 4 floats long
+        // (p.aligned = 2), 8-byte ones the same with 8 and 2 (p.aligned = 1, two-stage kernel only)
         constexpr int NN = F::EIGHT ? 8 : 4;
-        bool ia = (sys->nrows % 4 == 0) && (sys->batch_stride % 4 == 0);
-        auto a16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
-        for (int n = 0; n < NN; n++) ia = ia && a16(sys->w[n]);
-        for (int q = 0; q < F::NUNK; q++) ia = ia && a16(sys->x[q]) && a16(sys->c[q]) && a16(sys->d[q]) && (!F::LATE || a16(sys->x0[q]));
-        if (F::NUNK == 2) ia = ia && a16(sys->m);
-        p.aligned = ia ? 1 : 0;
+        auto al = [&](int vw) {
+            bool ia = (sys->nrows % vw == 0) && (sys->batch_stride % vw == 0);
+            auto ok = [&](const void *q) { return ((uintptr_t)q & (uintptr_t)(4 * vw - 1)) == 0; };
+            for (int n = 0; n < NN; n++) ia = ia && ok(sys->w[n]);
+            for (int q = 0; q < F::NUNK; q++) ia = ia && ok(sys->x[q]) && ok(sys->c[q]) && ok(sys->d[q]) && (!F::LATE || ok(sys->x0[q]));
+            if (F::NUNK == 2) ia = ia && ok(sys->m);
+            return ia;
+        };
+        p.aligned = al(4) ? 2 : al(2) ? 1 : 0;
     }
     {
         static const int gen = getenv("PDEGPU_ALR_WINDOW") ? atoi(getenv("PDEGPU_ALR_WINDOW")) : 2;
@@ -356,7 +363,8 @@ static int alr_window_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, f
     if (sys->nrows < 8 || sys->ncols < 8) return PDEGPU_ERR_UNSUPPORTED;
     // Lines that are not a multiple of 4 floats long take 4 scalar loads per vector: measured slower than
     // generation 1 once the problem is large enough to be bandwidth- rather than launch-bound.
-    if (((sys->nrows | sys->ncols) & 3) && (long long)sys->nrows * sys->ncols * sys->batch > (1ll << 20)) return PDEGPU_ERR_UNSUPPORTED;
+    // (even sizes take 8-byte vector loads in the two-stage kernel and stay here)
+    if (((sys->nrows | sys->ncols) & 1) && (long long)sys->nrows * sys->ncols * sys->batch > (1ll << 20)) return PDEGPU_ERR_UNSUPPORTED;
     if ((long long)sys->batch * sys->batch_stride >= (1ll << 31)) return PDEGPU_ERR_UNSUPPORTED;
     constexpr int NN = F::EIGHT ? 8 : 4;
     const long long npix = (long long)sys->nrows * sys->ncols;

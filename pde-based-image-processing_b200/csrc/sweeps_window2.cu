@@ -20,6 +20,7 @@
 namespace {
 
 constexpr int kW2Threads = 384;
+constexpr int kW2ThreadsV2 = 512;                             // the 8-byte-vector variant needs fewer registers: up to 16 warps
 constexpr int kW2MaxG = 4;                                   // at most 4 assembler warps per line
 
 // Phase probes (build with -DW2_PROBE; never in the shipped library): cycles per warp role, summed over all warps.
@@ -36,8 +37,10 @@ __device__ unsigned long long g_w2_probe[16];
 #define PROBE_USE(v)
 #endif
 
-template <int FAM, int DIR, int M, bool AL>
-__global__ void __launch_bounds__(kW2Threads, 1)
+// VW: pixels per lane and batch = width of the vector loads (4: 16-byte, needs lines of a multiple of 4 floats; 2: 8-byte,
+// for the even-sized pyramid levels); AL = false: VW scalar loads per vector (odd line lengths).
+template <int FAM, int DIR, int M, int VW, bool AL>
+__global__ void __launch_bounds__((VW == 2 && AL) ? kW2ThreadsV2 : kW2Threads, 1)
 alr_window2_kernel(const WinParams p)
 {
     using F = Fam<FAM>;
@@ -51,7 +54,6 @@ alr_window2_kernel(const WinParams p)
     // pixels per lane and batch, batches in flight per lane. Measured (B200, 64 x 480x640, us per pass, lines of 480 / 640):
     // VW 4 single-buffered 395 / 448, VW 2 double-buffered 411 / 542 (same bytes in flight per lane -- the register file
     // is the limit -- and twice the load instructions).
-    constexpr int VW = 4;
     constexpr int NT = (LS + 32 * VW - 1) / (32 * VW);
     constexpr int BUF = RF::N * LS;                           // floats per row buffer
     extern __shared__ float smem[];
@@ -254,7 +256,7 @@ alr_window2_kernel(const WinParams p)
                 for (int qq = 0; qq < NUNK; qq++) {
                     float *o = p.xout[qq] + (long long)T.img * p.ostride + j0;
                     const float *rq = rblk + qq * P;
-                    if (cnt == 8 && p.vec_ok) {
+                    if (cnt == 8 && p.vec_ok == 2) {
                         const int h = lane >> 4;
                         const float *rh = rq + (size_t)(4 * h) * SP;
 #pragma unroll 2
@@ -263,6 +265,14 @@ alr_window2_kernel(const WinParams p)
                             v.x = rh[i]; v.y = rh[SP + i]; v.z = rh[2 * SP + i]; v.w = rh[3 * SP + i];
                             *reinterpret_cast<float4 *>(o + (long long)i * nlines + 4 * h) = v;
                         }
+                    } else if (cnt == 8 && p.vec_ok == 1) {
+                        // X_out only 8-byte aligned (nlines even, not a multiple of 4): two lines per lane, still one
+                        // full 32-B sector per element and instruction
+                        const int h = lane >> 3;
+                        const float *rh = rq + (size_t)(2 * h) * SP;
+#pragma unroll 2
+                        for (int i = lane & 7; i < n; i += 8)
+                            *reinterpret_cast<float2 *>(o + (long long)i * nlines + 2 * h) = make_float2(rh[i], rh[SP + i]);
                     } else {
                         const int k = lane & 7;
                         for (int i = lane >> 3; i < n; i += 4)
@@ -282,19 +292,19 @@ alr_window2_kernel(const WinParams p)
     }
 }
 
-template <int FAM, int DIR, int M, bool AL>
+template <int FAM, int DIR, int M, int VW, bool AL>
 int launch_window2(pdegpu_ctx *ctx, const WinParams &p, size_t smem, int batch)
 {
     static bool attr_set[16] = {false};
     if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M, VW, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window2_kernel)");
         attr_set[ctx->device & 15] = true;
     }
     const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_window2_kernel<dir0>" : "alr_window2_kernel<dir1,transposed>",
                 sweep_bytes<FAM>() * (double)p.n * p.nlines * batch);
-    alr_window2_kernel<FAM, DIR, M, AL><<<grid, (p.NA + p.NS) * 32, smem, ctx->stream>>>(p);
+    alr_window2_kernel<FAM, DIR, M, VW, AL><<<grid, (p.NA + p.NS) * 32, smem, ctx->stream>>>(p);
     PDEGPU_LAUNCH_CHECK(ctx, "alr_window2_kernel");
     return PDEGPU_OK;
 }
@@ -307,11 +317,14 @@ int window2_dispatch(pdegpu_ctx *ctx, WinParams &p, int M, int nunk, int batch)
     const size_t room = 227 * 1024;
     static const int envNA = getenv("PDEGPU_W2_NA") ? atoi(getenv("PDEGPU_W2_NA")) : 8;       // tuning overrides (NA + NS <= 12)
     static const int envNS = getenv("PDEGPU_W2_NS") ? atoi(getenv("PDEGPU_W2_NS")) : 4;
-    p.NA = envNA; p.NS = envNS;
+    static const int envNA2 = getenv("PDEGPU_W2_NA2") ? atoi(getenv("PDEGPU_W2_NA2")) : 12;   // assembler warps of the 8-byte-vector variant (fewer registers: 16 warps fit)
+    static const int envVW = getenv("PDEGPU_W2_VW") ? atoi(getenv("PDEGPU_W2_VW")) : 0;        // 2: 8-byte vectors even where 16-byte ones are possible
+    if (envVW == 2 && p.aligned == 2) p.aligned = 1;
+    p.NA = p.aligned == 1 ? envNA2 : envNA; p.NS = envNS;
     static const int envG = getenv("PDEGPU_W2_G") ? atoi(getenv("PDEGPU_W2_G")) : 2;          // assembler warps per line (measured, us per pass 480 / 640: G=1 413 / 432, G=2 411 / 406, G=4 442 / 439)
     p.G = envG;
     if (p.G < 1 || p.G > kW2MaxG || p.NA % p.G) return PDEGPU_ERR_UNSUPPORTED;
-    if (p.NA < 1 || p.NS < 1 || p.NA + p.NS > kW2Threads / 32) return PDEGPU_ERR_UNSUPPORTED;
+    if (p.NA < 1 || p.NS < 1 || p.NA + p.NS > (p.aligned == 1 ? kW2ThreadsV2 : kW2Threads) / 32) return PDEGPU_ERR_UNSUPPORTED;
     static const int envR = getenv("PDEGPU_W2_R") ? atoi(getenv("PDEGPU_W2_R")) : 0;          // ring lines (multiple of 8) / even lead
     static const int envD = getenv("PDEGPU_W2_D") ? atoi(getenv("PDEGPU_W2_D")) : 0;
     static const int envNBUF = getenv("PDEGPU_W2_NBUF") ? atoi(getenv("PDEGPU_W2_NBUF")) : 8;
@@ -326,11 +339,11 @@ int window2_dispatch(pdegpu_ctx *ctx, WinParams &p, int M, int nunk, int batch)
         p.R = rd[0]; p.D = rd[1]; p.NBUF = nbuf;
         const size_t smem = fixed + (size_t)nbuf * rowf * LS * sizeof(float);
         switch (M) {
-        case 5: return p.aligned ? launch_window2<FAM, DIR, 5, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 5, false>(ctx, p, smem, batch);
-        case 9: return p.aligned ? launch_window2<FAM, DIR, 9, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 9, false>(ctx, p, smem, batch);
-        case 15: return p.aligned ? launch_window2<FAM, DIR, 15, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 15, false>(ctx, p, smem, batch);
-        case 21: return p.aligned ? launch_window2<FAM, DIR, 21, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 21, false>(ctx, p, smem, batch);
-        case 25: return p.aligned ? launch_window2<FAM, DIR, 25, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 25, false>(ctx, p, smem, batch);
+        case 5: return p.aligned == 2 ? launch_window2<FAM, DIR, 5, 4, true>(ctx, p, smem, batch) : p.aligned == 1 ? launch_window2<FAM, DIR, 5, 2, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 5, 4, false>(ctx, p, smem, batch);
+        case 9: return p.aligned == 2 ? launch_window2<FAM, DIR, 9, 4, true>(ctx, p, smem, batch) : p.aligned == 1 ? launch_window2<FAM, DIR, 9, 2, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 9, 4, false>(ctx, p, smem, batch);
+        case 15: return p.aligned == 2 ? launch_window2<FAM, DIR, 15, 4, true>(ctx, p, smem, batch) : p.aligned == 1 ? launch_window2<FAM, DIR, 15, 2, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 15, 4, false>(ctx, p, smem, batch);
+        case 21: return p.aligned == 2 ? launch_window2<FAM, DIR, 21, 4, true>(ctx, p, smem, batch) : p.aligned == 1 ? launch_window2<FAM, DIR, 21, 2, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 21, 4, false>(ctx, p, smem, batch);
+        case 25: return p.aligned == 2 ? launch_window2<FAM, DIR, 25, 4, true>(ctx, p, smem, batch) : p.aligned == 1 ? launch_window2<FAM, DIR, 25, 2, true>(ctx, p, smem, batch) : launch_window2<FAM, DIR, 25, 4, false>(ctx, p, smem, batch);
         default: return PDEGPU_ERR_UNSUPPORTED;
         }
     }

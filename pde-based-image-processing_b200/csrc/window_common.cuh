@@ -13,8 +13,8 @@ struct WinParams {
     int NB, TB;            // 8-line blocks per problem, in total
     int R, D;              // ring size in lines (multiple of 8), how many pairs the even lines run ahead
     int NA, NS, NBUF;      // two-stage kernel: assembler warps, solver warps, row buffers
-    int vec_ok;            // float4 stores of X_out are aligned
-    int aligned;           // float4 loads of the inputs are aligned (else 4 scalar loads per vector)
+    int vec_ok;            // stores of X_out: 2 = 16-byte aligned, 1 = 8-byte aligned, 0 = scalar
+    int aligned;           // vector loads of the inputs: 2 = 16-byte aligned, 1 = 8-byte aligned, 0 = scalar loads
     int G;                 // two-stage kernel: assembler warps per line
     float omega;
 };

@@ -1,4 +1,6 @@
 #!/bin/bash
 cd /root/repo
-timeout 500 python -m pytest tests/test_gpu_fullsize.py -x -q -m gpu < /dev/null 2>&1 | tail -12
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 python -m pytest tests/test_gpu_sweeps.py -x -q -m gpu -k "not 1080 and not 480" < /dev/null > gpurun_out/sanitizer_memcheck.log 2>&1; echo "memcheck rc $?"; tail -5 gpurun_out/sanitizer_memcheck.log
+timeout 400 python -m pytest tests/test_gpu_sweeps.py tests/test_gpu_pipeline.py -x -q -m gpu < /dev/null 2>&1 | tail -3
+P="timeout 120 python tools/w2_probe.py"
+for sz in "64 270 360" "16 270 360" "16 203 270" "16 66 88"; do echo "== batch nr nc = $sz"; $P $sz < /dev/null 2>&1 | grep "alr_\|transpose"; done
+timeout 300 python bench.py --steps 5 --warmup 3 < /dev/null > gpurun_out/bench_h2.json 2> gpurun_out/bench_h2.err; echo "bench rc $?"
