@@ -564,11 +564,18 @@ int alr_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 }  // namespace
 
 int relax_window_line(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega);
+int relax_tline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega);        // sweeps_tline.cu
 
 int relax_stream_line(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
     // generation 2 (sliding window, sweeps_window.cu) where it has a kernel; PDEGPU_ALR_WINDOW=0 disables it
     static const int use_window = getenv("PDEGPU_ALR_WINDOW") ? atoi(getenv("PDEGPU_ALR_WINDOW")) : 1;
+    // generation 3 (TMA-fed, total-field form, sweeps_tline.cu) first; PDEGPU_ALR_GEN=2 keeps generation 2
+    static const int gen = getenv("PDEGPU_ALR_GEN") ? atoi(getenv("PDEGPU_ALR_GEN")) : 3;
+    if (use_window && gen >= 3) {
+        const int rc = relax_tline(ctx, sys, iter, omega);
+        if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
+    }
     if (use_window) {
         const int rc = relax_window_line(ctx, sys, iter, omega);
         if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;

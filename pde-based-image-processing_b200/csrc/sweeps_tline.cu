@@ -1,0 +1,308 @@
+// sweeps_tline.cu -- kernel generation 3 of solver 2 (zebra line relaxation): preparation, sequencing of the
+// passes and recovery of the increment. Formulation and layouts: tline_common.cuh; pass kernel:
+// sweeps_tline_impl.cuh. Replaces, where it applies, generation 2 (sweeps_window*.cu) for
+// GS_ALR_SOR_elin4_2d / _llin4_2d / _llin8_2d (opticalflowSolvers.c:196,690,1677), the disparity
+// GS_ALR_SOR_llin4_2d (disparitySolvers.c:154) and GS_ALR_SOR_4_2d (pdeSolvers.c:277).
+#include "sweeps_tline_impl.cuh"
+#include <cstdlib>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// Preparation: the caller's dense column-major arrays -> packed lines of both passes (tline_common.cuh) + packed T lines.
+// One CTA per 32 x 32 tile and problem: every input of the tile is loaded up front (13 independent loads per pixel
+// in flight), the derived fields (T, C') are formed in registers, the column-pass lines are stored directly, the
+// row-pass lines through one shared tile per field (a single barrier). Pad elements of the pitched lines are written
+// as zeros: bulk copies never move uninitialised data.
+// ------------------------------------------------------------------------------------------------------------------
+struct PrepParams {
+    const float *w[8], *m, *c[2], *d[2], *x0[2], *x[2];
+    int nrows, ncols, pitch0, pitch1;
+    long long ibs;                           // floats between problems of the inputs
+    float *pn, *pt, *tn;                     // packed coefficient lines: column pass / row pass; packed T lines (column pass)
+};
+
+// C' = C + D x0 + M y0. Where the reference's row would produce NaN (a number for C next to a NaN D or M) C' stays a
+// number and the NaN reaches the row through D / M, as it does in the reference.
+__device__ __forceinline__ float tl_cprime(float C, float D, float M, float x0, float y0, bool late, bool flow)
+{
+    if (!late || is_nan(C) || is_nan(D) || (flow && is_nan(M))) return C;
+    float v = C + D * x0;
+    if (flow) v += M * y0;
+    return v;
+}
+
+template <int FAM>
+__global__ void __launch_bounds__(256)
+tline_prep_kernel(const PrepParams p)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4;
+    constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
+    constexpr int rDG = NUNK == 2 ? 9 : 6;
+    extern __shared__ float tiles[];                         // [NC][32][33], indexed by the row of the ROW-pass line
+    const int b = blockIdx.z;
+    const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int i = i0 + tx, ic = min(i, p.nrows - 1);
+    // rows of a packed line. Column pass (lines = Matlab columns): previous/next element = N/S, lines j-1 / j+1 = W/E,
+    // diagonals (LP, LN, HP, HN) = NW SW NE SE, first unknown first. Row pass (lines = Matlab rows): previous/next = W/E,
+    // lines i-1 / i+1 = N/S, diagonals NW NE SW SE, SECOND unknown first (the reference's pass order,
+    // opticalflowSolvers.c:735-754).
+    constexpr int wsrc[8] = {W_N, W_S, W_W, W_E, W_NW, W_SW, W_NE, W_SE};
+    constexpr int wrow0[8] = {TL_WP, TL_WN, TL_WL, TL_WH, rDG + 0, rDG + 1, rDG + 2, rDG + 3};
+    constexpr int wrow1[8] = {TL_WL, TL_WH, TL_WP, TL_WN, rDG + 0, rDG + 2, rDG + 1, rDG + 3};
+    float vw[4][NN], vm[4], vc[4][NUNK], vd[4][NUNK], vx0[4][NUNK], vx[4][NUNK];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int jc = min(j0 + ty + 8 * r, p.ncols - 1);
+        const long long src = (long long)b * p.ibs + (long long)jc * p.nrows + ic;
+#pragma unroll
+        for (int k = 0; k < NN; k++) vw[r][k] = p.w[wsrc[k] % NN == wsrc[k] ? wsrc[k] : 0][src];
+        vm[r] = NUNK == 2 ? p.m[src] : 0.f;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            vc[r][q] = p.c[q][src]; vd[r][q] = p.d[q][src]; vx[r][q] = p.x[q][src];
+            vx0[r][q] = F::LATE ? p.x0[q][src] : 0.f;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int j = j0 + ty + 8 * r;
+        const bool st = i < p.pitch0 && j < p.ncols, in = i < p.nrows;
+        float *ln = p.pn + ((long long)b * p.ncols + min(j, p.ncols - 1)) * NC * p.pitch0 + i;
+        float *lt = p.tn + ((long long)b * p.ncols + min(j, p.ncols - 1)) * NUNK * p.pitch0 + i;
+        auto put = [&](int row0, int row1, float v) {
+            if (st) ln[(long long)row0 * p.pitch0] = in ? v : 0.f;
+            tiles[(row1 * 32 + ty + 8 * r) * 33 + tx] = v;
+        };
+#pragma unroll
+        for (int k = 0; k < NN; k++) put(wrow0[k], wrow1[k], vw[r][k]);
+        if (NUNK == 2) put(TL_MM, TL_MM, vm[r]);
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            const int r0 = 3 * q, r1 = NUNK == 2 ? 3 * (1 - q) : 0;              // unknown q is solved q-th / (1-q)-th
+            put(TL_D0 + r0, TL_D0 + r1, vd[r][q]);
+            put(TL_C0 + r0, TL_C0 + r1, tl_cprime(vc[r][q], vd[r][q], vm[r], vx0[r][q], vx0[r][NUNK - 1 - q], F::LATE, NUNK == 2));
+            if (st) lt[(long long)q * p.pitch0] = in ? (F::LATE ? vx0[r][q] + vx[r][q] : vx[r][q]) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int jj = j0 + tx;
+    if (jj < p.pitch1) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int ii = i0 + ty + 8 * r;
+            if (ii < p.nrows) {
+                float *l1 = p.pt + ((long long)b * p.nrows + ii) * NC * p.pitch1 + jj;
+#pragma unroll
+                for (int f = 0; f < NC; f++) l1[(long long)f * p.pitch1] = jj < p.ncols ? tiles[(f * 32 + tx) * 33 + ty + 8 * r] : 0.f;
+            }
+        }
+    }
+}
+
+// x = T - x0 (late linearisation) or x = T, from the packed T lines back into the caller's dense arrays
+struct FinalParams { float *x[2]; const float *x0[2]; const float *tn; int nunk; int nrows, ncols, pitch0, vec; long long xbs; };
+
+static __global__ void __launch_bounds__(256)
+tline_final_kernel(const FinalParams p)
+{
+    const int b = blockIdx.z, j = blockIdx.y;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= p.nrows) return;
+    const long long d = (long long)b * p.xbs + (long long)j * p.nrows + i;
+    for (int q = 0; q < p.nunk; q++) {
+        const float *t = p.tn + (((long long)b * p.ncols + j) * p.nunk + q) * p.pitch0 + i;
+        if (p.vec) {                                          // 16-byte aligned caller arrays, lines a multiple of 4 long
+            float4 v = *reinterpret_cast<const float4 *>(t);
+            if (p.x0[q]) {
+                const float4 u = *reinterpret_cast<const float4 *>(p.x0[q] + d);
+                v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w;
+            }
+            *reinterpret_cast<float4 *>(p.x[q] + d) = v;
+        } else {
+            for (int k = 0; k < 4 && i + k < p.nrows; k++) p.x[q][d + k] = t[k] - (p.x0[q] ? p.x0[q][d + k] : 0.f);
+        }
+    }
+}
+
+struct TLGeom { int M, R, D, K, BL, NBR, NCW, SP; size_t smem; };
+
+static int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// Shared memory of one SM: the T ring (R lines), K coefficient slabs, barriers. Preference: the roomiest ring that
+// still leaves 5 slabs, else the geometry with most slabs.
+static bool tline_geometry(int n, int nunk, int nc, TLGeom &g)
+{
+    static const int Ms[] = {5, 9, 15, 17, 21, 25};
+    g.M = 0;
+    for (int m : Ms) if (32 * m >= n) { g.M = m; break; }
+    if (!g.M || n < 8) return false;
+    const int P = (n + 3) & ~3;
+    const size_t room = 227 * 1024;
+    static const int eBL = env_int("PDEGPU_TL_BL", 0), eR = env_int("PDEGPU_TL_R", 0), eD = env_int("PDEGPU_TL_D", 0), eK = env_int("PDEGPU_TL_K", 0);
+    static const int eNCW = env_int("PDEGPU_TL_NCW", 0);
+    const int total_warps = g.M <= 9 ? 16 : g.M <= 17 ? 12 : 8;
+    g.NCW = eNCW > 0 && eNCW <= total_warps - 2 ? eNCW : total_warps - 2;
+    // ring entries 4 floats apart from a multiple of 8: the two half-warps of a block write (lines 4h..4h+3) then read
+    // different banks
+    g.SP = nunk * P + ((nunk * P) % 8 == 0 ? 4 : 0);
+    const size_t line = (size_t)g.SP * 4, slab = (size_t)nc * P * 4;
+    // Candidates (BL, R, D), best first; the first that leaves 3 slabs wins. Measured (B200, 64 x 480x640, us per pass at
+    // 480 / 640 elements): blocks of 8 lines (full 32-byte sectors in the transposed write) 223 / 229 against 268 / 285 for
+    // blocks of 4; 4 to 8 slabs and rings of 24 to 32 lines within 3 % of each other once the slab is given back right
+    // after the row formulas (profiles/r02_tline_sweep.txt).
+    const int cand[][3] = {{8, 24, 4}, {8, 16, 4}, {4, 16, 3}, {4, 12, 2}, {4, 8, 2}};
+    int bestK = 0;
+    for (auto &c : cand) {
+        const int BL = eBL ? eBL : c[0], R = eR ? eR : c[1], D = eD ? eD : c[2];
+        if (R % BL || R < 2 * D + BL || (BL != 4 && BL != 8)) continue;
+        const int NBR = R / BL + 2;
+        const size_t fixed = (size_t)R * line + 2 * (size_t)((32 * g.M - n + 3) & ~3) * 4 + (size_t)(2 * R) * 8 + (size_t)(2 * NBR + 4) * 4 + 64;
+        if (fixed >= room) continue;
+        int K = (int)((room - fixed) / (slab + 16 + 32));
+        if (K > 8) K = 8;
+        if (eK && eK < K) K = eK;
+        if (K < 2 || K <= bestK) continue;
+        bestK = K;
+        g.BL = BL; g.R = R; g.D = D; g.K = K; g.NBR = NBR;
+        g.smem = fixed + (size_t)K * (slab + 16 + 32);
+        if (K >= 3) break;
+    }
+    return bestK > 0;
+}
+
+template <int NUNK, int NN, int MODE, int M>
+int tline_launch(pdegpu_ctx *ctx, const TLParams &p, const TLGeom &g, double bytes, const char *name)
+{
+    cudaError_t e = cudaFuncSetAttribute(tline_pass_kernel<NUNK, NN, MODE, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_pass_kernel)");
+    const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
+    PDEGPU_PROF(ctx, name, bytes);
+    tline_pass_kernel<NUNK, NN, MODE, M><<<grid, (g.NCW + 2) * 32, g.smem, ctx->stream>>>(p);
+    PDEGPU_LAUNCH_CHECK(ctx, "tline_pass_kernel");
+    return PDEGPU_OK;
+}
+
+template <int NUNK, int NN, int MODE>
+int tline_pass(pdegpu_ctx *ctx, TLParams &p, int batch, double bytes, const char *name)
+{
+    constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
+    TLGeom g;
+    if (!tline_geometry(p.n, NUNK, NC, g)) return PDEGPU_ERR_UNSUPPORTED;
+    p.BL = g.BL; p.R = g.R; p.D = g.D; p.K = g.K; p.NBR = g.NBR; p.NCW = g.NCW; p.SP = g.SP;
+    p.NB = (p.nlines + g.BL - 1) / g.BL; p.TB = p.NB * batch;
+    switch (g.M) {
+    case 5:  return tline_launch<NUNK, NN, MODE, 5>(ctx, p, g, bytes, name);
+    case 9:  return tline_launch<NUNK, NN, MODE, 9>(ctx, p, g, bytes, name);
+    case 15: return tline_launch<NUNK, NN, MODE, 15>(ctx, p, g, bytes, name);
+    case 17: return tline_launch<NUNK, NN, MODE, 17>(ctx, p, g, bytes, name);
+    case 21: return tline_launch<NUNK, NN, MODE, 21>(ctx, p, g, bytes, name);
+    case 25: return tline_launch<NUNK, NN, MODE, 25>(ctx, p, g, bytes, name);
+    default: return PDEGPU_ERR_UNSUPPORTED;
+    }
+}
+
+template <int FAM>
+int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, MODE = F::PDE ? 1 : 0;
+    constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
+    const int nr = sys->nrows, nc = sys->ncols, batch = sys->batch;
+    if (iter <= 0) return PDEGPU_OK;
+    if (nr < 8 || nc < 8 || nr > 800 || nc > 800 || batch > 65535) return PDEGPU_ERR_UNSUPPORTED;
+    if (F::PDE && F::EIGHT) return PDEGPU_ERR_UNSUPPORTED;    // NaN-TRACE diagonal of pdeSolvers.c:1179 not restated here
+    TLGeom g0, g1;
+    if (!tline_geometry(nr, NUNK, NC, g0) || !tline_geometry(nc, NUNK, NC, g1)) return PDEGPU_ERR_UNSUPPORTED;
+    const int pitch0 = (nr + 3) & ~3, pitch1 = (nc + 3) & ~3;
+    const long long S0 = (long long)nc * pitch0, S1 = (long long)nr * pitch1;   // floats per field and problem, column / row pass layout
+    if ((long long)batch * NC * (S0 > S1 ? S0 : S1) >= (1ll << 40)) return PDEGPU_ERR_UNSUPPORTED;
+
+    // scratch: packed coefficient lines of both passes, packed T lines of both passes
+    const size_t bytes_pn = (size_t)NC * S0 * batch * 4, bytes_pt = (size_t)NC * S1 * batch * 4;
+    const size_t bytes_tn = (size_t)NUNK * S0 * batch * 4, bytes_tt = (size_t)NUNK * S1 * batch * 4;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    int rc = pdegpu_scratch_reserve(ctx, up(bytes_pn) + up(bytes_pt) + up(bytes_tn) + up(bytes_tt));
+    if (rc) return rc;
+    char *sp = ctx->scratch;
+    float *PN = (float *)sp; sp += up(bytes_pn);
+    float *PT = (float *)sp; sp += up(bytes_pt);
+    float *TN = (float *)sp; sp += up(bytes_tn);
+    float *TT = (float *)sp;
+
+    {
+        PrepParams pp;
+        memset(&pp, 0, sizeof(pp));
+        for (int k = 0; k < NN; k++) pp.w[k] = sys->w[k];
+        pp.m = sys->m;
+        for (int q = 0; q < NUNK; q++) { pp.c[q] = sys->c[q]; pp.d[q] = sys->d[q]; pp.x0[q] = sys->x0[q]; pp.x[q] = sys->x[q]; }
+        pp.nrows = nr; pp.ncols = nc; pp.pitch0 = pitch0; pp.pitch1 = pitch1;
+        pp.ibs = sys->batch_stride; pp.pn = PN; pp.pt = PT; pp.tn = TN;
+        const size_t smem = (size_t)NC * 32 * 33 * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
+        dim3 grid((nr + 31) / 32, (nc + 31) / 32, batch);
+        const double fields_in = NN + (NUNK == 2 ? 1 : 0) + NUNK * (F::LATE ? 4 : 3), fields_out = 2 * NC + NUNK;
+        PDEGPU_PROF(ctx, "tline_prep_kernel", 4.0 * (fields_in + fields_out) * nr * nc * batch);
+        tline_prep_kernel<FAM><<<grid, 256, smem, ctx->stream>>>(pp);
+        PDEGPU_LAUNCH_CHECK(ctx, "tline_prep_kernel");
+    }
+
+    TLParams p0, p1;
+    memset(&p0, 0, sizeof(p0));
+    p0.coef = PN; p0.tin = TN; p0.tout = TT; p0.obs = (long long)NUNK * S1;
+    p0.pitch = pitch0; p0.opitch = pitch1; p0.q0 = 0; p0.n = nr; p0.nlines = nc; p0.omega = omega;
+    p1 = p0;
+    p1.coef = PT; p1.tin = TT; p1.tout = TN; p1.obs = (long long)NUNK * S0;
+    p1.pitch = pitch1; p1.opitch = pitch0; p1.q0 = NUNK == 2 ? 1 : 0; p1.n = nc; p1.nlines = nr;
+
+    const double pass_bytes = sweep_bytes<FAM>() * (double)nr * nc * batch;
+    for (int it = 0; it < iter; it++) {
+        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p0, batch, pass_bytes, "tline_pass_kernel<dir0>"))) return rc;
+        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p1, batch, pass_bytes, "tline_pass_kernel<dir1,transposed>"))) return rc;
+    }
+    {
+        FinalParams fp;
+        memset(&fp, 0, sizeof(fp));
+        for (int q = 0; q < NUNK; q++) { fp.x[q] = sys->x[q]; fp.x0[q] = F::LATE ? sys->x0[q] : nullptr; }
+        fp.tn = TN; fp.nunk = NUNK; fp.nrows = nr; fp.ncols = nc; fp.pitch0 = pitch0; fp.xbs = sys->batch_stride;
+        bool vec = (nr % 4 == 0) && (sys->batch_stride % 4 == 0);
+        for (int q = 0; q < NUNK; q++) vec = vec && (((uintptr_t)sys->x[q] | (uintptr_t)(F::LATE ? sys->x0[q] : nullptr)) & 15) == 0;
+        fp.vec = vec ? 1 : 0;
+        dim3 grid((nr + 1023) / 1024, nc, batch);
+        PDEGPU_PROF(ctx, "tline_final_kernel", 4.0 * NUNK * (F::LATE ? 3 : 2) * nr * nc * batch);
+        tline_final_kernel<<<grid, 256, 0, ctx->stream>>>(fp);
+        PDEGPU_LAUNCH_CHECK(ctx, "tline_final_kernel");
+    }
+    return PDEGPU_OK;
+}
+
+}  // namespace
+
+#ifdef TL_PROBE
+extern "C" int pdegpu_debug_tl_probe(unsigned long long *out32)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out32, g_tl_probe, sizeof(g_tl_probe)) != cudaSuccess) return -1;
+    unsigned long long z[32] = {0};
+    return cudaMemcpyToSymbol(g_tl_probe, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+int relax_tline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    switch (sys->family) {
+    case PDEGPU_FLOW_ELIN4: return tline_run<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN4: return tline_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN8: return tline_run<PDEGPU_FLOW_LLIN8>(ctx, sys, iter, omega);
+    case PDEGPU_DISP_LLIN4: return tline_run<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE4:       return tline_run<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    default: return PDEGPU_ERR_UNSUPPORTED;
+    }
+}
