@@ -45,6 +45,10 @@ ITER, OMEGA, SOLVER = 4, 1.9, 2    # driver defaults
 FN = "Oflow_sor_llin4_2d"
 B1_LLIN4 = 60.0                    # algorithmic bytes / px / sweep
 METRIC = "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, ALR)"
+
+
+def metric_name(solver):
+    return METRIC if solver == 2 else "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, red-black point SOR)"
 UNIT = "Mpix*iter/s"
 
 
@@ -74,6 +78,7 @@ def parse():
     ap.add_argument("--band-iters", type=int, default=8, help="red-black sweeps per step")
     ap.add_argument("--band-T", type=int, default=1, help="sweeps per halo exchange (halo = 2T columns)")
     ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
+    ap.add_argument("--sweep-legs", type=int, default=1, help="relaxation sweep alone at 1080p / 4096x2160 / point solver (0 = skip)")
     ap.add_argument("--fmg-pairs", type=int, default=2, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
     return ap.parse_args()
 
@@ -129,6 +134,9 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the reference's own CPU code on the host cores
 # ---------------------------------------------------------------------------------------------
+_WORKER_LIBS = []
+
+
 def cpu_reference_throughput(seconds_target=10.0, calls_per_worker=None):
     """Times mex_Oflow_sor_llin4_2d of the unmodified reference (oracle/_ref) on independent 480x640
     systems, one worker per host core (the reference's sweep is single-threaded; a batch of pairs is
@@ -143,15 +151,19 @@ def cpu_reference_throughput(seconds_target=10.0, calls_per_worker=None):
 
     def make_worker():
         if kind == "reference":
-            # one private copy of the shared object per worker: the mex shim keeps per-library state
+            # one private copy of the shared object per worker (the mex shim keeps per-library state), kept inside
+            # oracle/_ref so that what the reference arm maps is visibly the reference
             import shutil
-            import tempfile
-            src = os.path.join(ROOT, "oracle", "_ref", "ref_oflow.so")
-            tmp = tempfile.NamedTemporaryFile(suffix=".so", delete=False)
-            tmp.close()
-            shutil.copy(src, tmp.name)
+            refdir = os.path.join(ROOT, "oracle", "_ref")
+            src = os.path.join(refdir, "ref_oflow.so")
+            wdir = os.path.join(refdir, "workers")
+            os.makedirs(wdir, exist_ok=True)
+            dst = os.path.join(wdir, f"ref_oflow.{len(_WORKER_LIBS)}.so")
+            if not (os.path.exists(dst) and os.path.getsize(dst) == os.path.getsize(src)):
+                shutil.copy(src, dst)
+            _WORKER_LIBS.append(dst)
             from pdegpu.mex_harness import MexLibrary
-            L = MexLibrary(tmp.name)
+            L = MexLibrary(dst)
             return lambda: L.call("mex_" + FN, args, 2)
         be = orc.OracleBackend()
         return lambda: be.call(FN, args, 2)
@@ -170,6 +182,7 @@ def cpu_reference_throughput(seconds_target=10.0, calls_per_worker=None):
     with ThreadPoolExecutor(max_workers=cores) as ex:
         list(ex.map(run, workers))
     dt = time.perf_counter() - t0
+    del _WORKER_LIBS[:]                      # the copies stay in oracle/_ref/workers (git-ignored) for the next call
     units = cores * n * NROWS * NCOLS * ITER / 1e6
     return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"{cores} workers x {n} calls of {FN} (480x640, iter={ITER}, omega={OMEGA}, solver={SOLVER}) "
@@ -371,6 +384,126 @@ def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
                                "sample": f"1 pair through oracle/pipelines.py (numpy restatement of the .m driver around the "
                                          f"{be.name} MEX code), {dt:.1f} s",
                                "aee_vs_ground_truth_px": aee_of(Uo, Vo)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sweep legs: the relaxation sweep alone at the shapes of the other BASELINE configs, each with
+# the roofline of its own dominant kernel. Systems are generated on the device (structurally valid: edge-symmetric
+# weights, positive semi-definite data term, 1 % NaN data terms).
+# ---------------------------------------------------------------------------------------------
+def device_system(torch, dev, fam, nr, nc, batch, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    shape = (batch, nc, nr)                       # column-major problems: [problem][j][i]
+    r = lambda lo, span: lo + span * torch.rand(shape, device=dev, generator=g)
+    f = {}
+    h, v = r(0.2, 3.0), r(0.2, 3.0)
+    f["wE"] = h.clone(); f["wE"][:, -1, :] = 0
+    f["wW"] = torch.zeros_like(h); f["wW"][:, 1:, :] = h[:, :-1, :]
+    f["wS"] = v.clone(); f["wS"][:, :, -1] = 0
+    f["wN"] = torch.zeros_like(v); f["wN"][:, :, 1:] = v[:, :, :-1]
+    del h, v
+    ix, iy, it = r(-0.5, 1), r(-0.5, 1), r(-0.5, 1)
+    gd = torch.clamp(1.0 / torch.sqrt(it * it + 1e-5), max=50.0)
+    nan = torch.rand(shape, device=dev, generator=g) < 0.01
+    if fam in ("elin4", "llin4"):
+        f.update({"M": gd * ix * iy, "Cu": -gd * it * ix, "Cv": -gd * it * iy, "Du": gd * ix * ix, "Dv": gd * iy * iy})
+        for k in ("M", "Cu", "Cv", "Du", "Dv"):
+            f[k][nan] = float("nan")
+        f["U"], f["V"] = r(-2, 4), r(-2, 4)
+        f["dU"], f["dV"] = r(-0.05, 0.1), r(-0.05, 0.1)
+    elif fam == "disp":
+        f.update({"Cu": -gd * it * ix, "Du": gd * ix * ix})
+        f["Cu"][nan] = float("nan"); f["Du"][nan] = float("nan")
+        f["U"], f["dU"] = r(-4, 8), r(-0.05, 0.1)
+    else:                                         # pde4: TRACE = sum of weights + data weight, B = data weight * image
+        psi, img = r(0.5, 1.0), r(0, 1)
+        f["TRACE"] = f["wW"] + f["wE"] + f["wN"] + f["wS"] + psi
+        f["TRACE"][nan] = float("nan")
+        f["B"] = psi * img
+        f["X"] = img + 0.05 * torch.randn(shape, device=dev, generator=g)
+    return f
+
+
+def device_sysd(lib, fam, f, nr, nc, batch):
+    n = nr * nc
+    w = [f[k].data_ptr() for k in ("wW", "wN", "wE", "wS")]
+    if fam == "elin4":
+        return lib.make_system(lib.FLOW_ELIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(), f["dV"].data_ptr()),
+                               m=f["M"].data_ptr(), c=(f["Cu"].data_ptr(), f["Cv"].data_ptr()), d=(f["Du"].data_ptr(), f["Dv"].data_ptr()), w=w), ("dU", "dV")
+    if fam == "llin4":
+        return lib.make_system(lib.FLOW_LLIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(), f["dV"].data_ptr()),
+                               x0=(f["U"].data_ptr(), f["V"].data_ptr()), m=f["M"].data_ptr(), c=(f["Cu"].data_ptr(), f["Cv"].data_ptr()),
+                               d=(f["Du"].data_ptr(), f["Dv"].data_ptr()), w=w), ("dU", "dV")
+    if fam == "disp":
+        return lib.make_system(lib.DISP_LLIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(),), x0=(f["U"].data_ptr(),),
+                               c=(f["Cu"].data_ptr(),), d=(f["Du"].data_ptr(),), w=w), ("dU",)
+    return lib.make_system(lib.PDE4, nr, nc, batch=batch, batch_stride=n, x=(f["X"].data_ptr(),),
+                           c=(f["B"].data_ptr(),), d=(f["TRACE"].data_ptr(),), w=w), ("X",)
+
+
+SWEEP_LEGS = [
+    # name, reference function it stands for, family, nrows, ncols, problems per GPU, solver, iter, omega, B1
+    ("sweep_1080p", "Oflow_sor_elin4_2d (finest level of configs[2], FlowEminNDFASFMG_elin_2D_v10.m:367-464)", "elin4", 1080, 1920, 8, 2, 4, 1.9, 52.0),
+    ("sweep_4096x2160", "Disp_sor_llin_sym4_2d = two Disp llin4 systems (finest level of configs[3], DispEminND_llin_sym_2D.m:227-246)", "disp", 2160, 4096, 4, 2, 4, 1.9, 36.0),
+    ("sweep_tv_4096x2160", "PDEsolver4 (TVdenoise4.m:85-90 at the configs[3] image size)", "pde4", 2160, 4096, 4, 2, 4, 1.75, 32.0),
+    ("point_480x640", "Oflow_sor_llin4_2d solver 1 (red-black point SOR)", "llin4", 480, 640, 64, 1, 4, 1.9, 60.0),
+]
+
+
+def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
+    import torch
+    from pdegpu import lib
+    peak, peak_src = measured_peaks()
+    out = {}
+    for name, what, fam, nr, nc, batch, solver, iters, omega, b1 in SWEEP_LEGS:
+        f = device_system(torch, dev, fam, nr, nc, batch, 777 + rank)
+        sysd, unk = device_sysd(lib, fam, f, nr, nc, batch)
+        x0 = [f[k].clone() for k in unk]
+
+        def barrier():
+            ctx.sync()
+            torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+
+        for _ in range(3):
+            ctx.relax(sysd, iters, omega, solver)
+        for k, v in zip(unk, x0):
+            f[k].copy_(v)
+        barrier()
+        ctx.profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            ctx.relax(sysd, iters, omega, solver)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        prof = ctx.profile_report()
+        ctx.profile(False)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        assert torch.isfinite(f[unk[0]]).all()
+        top = max((p for p in prof if p["bytes_total"] > 0 and "prep" not in p["kernel"] and "final" not in p["kernel"] and "transpose" not in p["kernel"]),
+                  key=lambda p: p["ms_total"], default=None)
+        leg = {"what": what, "family": fam, "nrows": nr, "ncols": nc, "problems_per_gpu": batch, "solver": solver, "iter": iters, "omega": omega,
+               "value": world * batch * nr * nc * iters * steps / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_call": ms / steps,
+               "l2": f"{(b1 / 4) * batch * nr * nc * 4 / 1e6:.0f} MB of fields per sweep vs 126 MB L2",
+               "algorithmic_bytes_per_px_sweep": b1,
+               "whole_call_frac_of_peak": (world * batch * nr * nc * iters * steps * b1 * (2 if solver == 2 else 1)) / (ms * 1e-3) / 1e9 / peak / world}
+        if top:
+            ach = top["bytes_total"] / (top["ms_total"] * 1e-3) / 1e9
+            leg["roofline"] = {"bound": "hbm", "kernel": top["kernel"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                               "peak_source": peak_src, "launch_ms_avg": top["ms_total"] / top["launches"], "launches": top["launches"],
+                               "algorithmic_bytes_per_launch": top["bytes_total"] / top["launches"], "traffic": None}
+        leg["kernels"] = prof
+        out[name] = leg
+        del f, x0
+        torch.cuda.empty_cache()
     return out
 
 
@@ -579,6 +712,7 @@ def run_ours(args):
 
     flows = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_batch) if args.flow_batch > 0 else None
     fmg = fmg_leg(ctx, dev, stream, dist, world, rank, args.fmg_pairs) if args.fmg_pairs > 0 else None
+    sweeps = sweep_legs(ctx, dev, stream, dist, world, rank) if args.sweep_legs else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -604,7 +738,7 @@ def run_ours(args):
                 pass
         cpu, _ = cpu_reference_throughput(seconds_target=10.0) if world == 1 else (None, 0)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args.solver), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[1]: Oflow_sor_llin4_2d inner solve of the 640x480 late-linearisation flow; "
@@ -621,6 +755,7 @@ def run_ours(args):
             "roofline": roof,
             "flows": flows,
             "fmg": fmg,
+            "sweeps": sweeps,
             "kernels": prof,
             "clocks": clocks,
         }

@@ -87,7 +87,7 @@ static void pdegpu_graphs_drop(pdegpu_ctx *ctx)
 int pdegpu_graph_run(pdegpu_ctx *ctx, const void *key, size_t key_len, pdegpu_graph_body body)
 {
     static const int enabled = getenv("PDEGPU_GRAPHS") ? atoi(getenv("PDEGPU_GRAPHS")) : 1;
-    static unsigned long long tick = 0;
+    unsigned long long &tick = ctx->graph_tick;             // least-recently-used clock of this context's cache
     if (!enabled || ctx->prof_on || ctx->capturing || key_len > (size_t)kGraphKeyMax) return body.fn(body.arg);
     if (!ctx->graphs) {
         ctx->graphs = (pdegpu_graph_entry *)calloc(kGraphSlots, sizeof(pdegpu_graph_entry));
@@ -235,6 +235,7 @@ extern "C" int pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen)
 extern "C" int pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path)
 {
     if (!ctx || path < 0 || path > 1) return PDEGPU_ERR_ARG;
+    if (ctx->kernel_path != path) ctx->graph_epoch++;      // captured graphs hold the other path's kernels
     ctx->kernel_path = path;
     return PDEGPU_OK;
 }

@@ -327,9 +327,10 @@ medfilt3_kernel(float *__restrict__ out, const float *__restrict__ in, int nr, i
     out[(long long)blockIdx.z * stride + (long long)j * nr + i] = v[4];
 }
 
-// out = a*x + b*y (single, one rounding per operation); y may be null (b ignored)
+// out = a*x + b*y (single, one rounding per operation); y may be null (b ignored). The pipelines call it in place
+// (out == x or out == y): no __restrict__ on purpose.
 __global__ void __launch_bounds__(256)
-axpby_kernel(float *__restrict__ out, float a, const float *__restrict__ x, float b, const float *__restrict__ y, long long n)
+axpby_kernel(float *out, float a, const float *x, float b, const float *y, long long n)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;

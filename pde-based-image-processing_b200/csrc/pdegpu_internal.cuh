@@ -35,6 +35,7 @@ struct pdegpu_ctx {
     // CUDA graphs of whole driver pipelines (pdegpu_graph_run): device pointers are baked in, so every reallocation of
     // arena / scratch / work bumps the epoch and the cached graphs die
     unsigned      graph_epoch;
+    unsigned long long graph_tick;
     int           capturing;
     struct pdegpu_graph_entry *graphs;
     char          err[512];

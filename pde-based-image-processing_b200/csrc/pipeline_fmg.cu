@@ -209,7 +209,8 @@ int fmg_run(pdegpu_ctx *ctx, Stack &b, float *Uout, float *Vout, const float *I0
             if (n.nr <= 10 || n.nc <= 10) break;
         }
         f.S = (int)f.L.size();
-        if (f.L.back().nr < 3 || f.L.back().nc < 3) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "flow_fmg: coarsest level smaller than 3 pixels");
+        // the 5-tap derivative stack of every level needs 5 pixels per dimension (imageDerivatives.c:66-211)
+        if (f.L.back().nr < 5 || f.L.back().nc < 5) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "flow_fmg: coarsest level smaller than 5 pixels (lower max_scales)");
     }
     const int S = f.S;
     const size_t n0 = f.L[0].n;
@@ -287,6 +288,11 @@ extern "C" int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const
     if (nrows < 8 || ncols < 8 || channels < 1 || batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "pdegpu_dev_flow_fmg_2d: bad shape");
     if (!(params->scl_factor > 0.0) || params->firstLoop < 1 || params->cycle_index < 1 || params->cycle_index > 2)
         return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_flow_fmg_2d: bad parameters");
+    // The pyramid, the restriction and the level sizes are the driver's 1:2:end decimation (FlowEminNDFASFMG_elin_2D_v10.m:106-118,
+    // 212-217); scl_factor only scales the restricted quantities and the prolongated correction, so any other value would
+    // describe an inconsistent multigrid (the reference fails on a size mismatch there).
+    if (fabs(params->scl_factor - 0.5) > 1e-12)
+        return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_flow_fmg_2d: scl_factor must be 0.5 (the pyramid is decimated 1:2)");
     PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     Stack dry = {nullptr, 0, 0, true};
     int rc = fmg_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);

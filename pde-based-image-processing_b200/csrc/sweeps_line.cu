@@ -236,11 +236,9 @@ template <int FAM, int DIR, int G, int TPL = (G >= 8 ? 32 : PDEGPU_ALR_TPL)>
 int launch_alr(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys, int colour, float omega,
                int first, int nslots, int n, int Lc, int Lp, size_t smem)
 {
-    static bool attr_set[16] = {false};
-    if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_kernel<FAM, DIR, G, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_kernel)");
-        attr_set[ctx->device & 15] = true;
+    {   // every launch: the attribute is per device and the call is cheap (no static per-ordinal bookkeeping)
+    cudaError_t e = cudaFuncSetAttribute(alr_kernel<FAM, DIR, G, TPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_kernel)");
     }
     dim3 grid((nslots + G - 1) / G, sys->batch);
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_kernel<dir0>" : DIR == 1 ? "alr_kernel<dir1>" : "alr_kernel<dir1,transposed>", sweep_bytes<FAM>() * (double)nslots * n * sys->batch);
@@ -403,11 +401,9 @@ int launch_alr_pipe(pdegpu_ctx *ctx, const SysView &v, const pdegpu_system *sys,
                     int first, int nslots, int n, int Lc, int Lp, size_t smem)
 {
     constexpr int NLW = 16;
-    static bool attr_set[16] = {false};
-    if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_pipe_kernel<FAM, DIR, G, NLW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_pipe_kernel)");
-        attr_set[ctx->device & 15] = true;
+    {   // every launch: the attribute is per device and the call is cheap (no static per-ordinal bookkeeping)
+    cudaError_t e = cudaFuncSetAttribute(alr_pipe_kernel<FAM, DIR, G, NLW, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_pipe_kernel)");
     }
     const int gpi = (nslots + G - 1) / G;
     const int total = gpi * sys->batch;

@@ -417,11 +417,9 @@ int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     if (NUNK == 2) al = al && a16(sys->m);
     static const int use_async = getenv("PDEGPU_POINT_ASYNC") ? atoi(getenv("PDEGPU_POINT_ASYNC")) : 1;
     if (al && use_async) {
-        static bool attr_set[16] = {false};
-        if (!attr_set[ctx->device & 15]) {
-            cudaError_t e = cudaFuncSetAttribute(rb_tile_async_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pt_async_floats<FAM>() * sizeof(float)));
-            if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(rb_tile_async_kernel)");
-            attr_set[ctx->device & 15] = true;
+        {   // every launch: the attribute is per device and the call is cheap (no static per-ordinal bookkeeping)
+        cudaError_t e = cudaFuncSetAttribute(rb_tile_async_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(pt_async_floats<FAM>() * sizeof(float)));
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(rb_tile_async_kernel)");
         }
     }
     SysView v = make_view(sys);

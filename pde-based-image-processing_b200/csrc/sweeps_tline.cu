@@ -18,6 +18,7 @@ namespace {
 struct PrepParams {
     const float *w[8], *m, *c[2], *d[2], *x0[2], *x[2];
     int nrows, ncols, pitch0, pitch1;
+    int S0, ns0, S1, ns1;                    // segments per line and their length: column pass (cuts along i), row pass (along j)
     long long ibs;                           // floats between problems of the inputs
     float *pn, *pt, *tn;                     // packed coefficient lines: column pass / row pass; packed T lines (column pass)
 };
@@ -45,6 +46,7 @@ tline_prep_kernel(const PrepParams p)
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int i = i0 + tx, ic = min(i, p.nrows - 1);
+    const int seg0 = min(i / p.ns0, p.S0 - 1), io = i - seg0 * p.ns0;          // segment of the column-pass line, element in it
     // rows of a packed line. Column pass (lines = Matlab columns): previous/next element = N/S, lines j-1 / j+1 = W/E,
     // diagonals (LP, LN, HP, HN) = NW SW NE SE, first unknown first. Row pass (lines = Matlab rows): previous/next = W/E,
     // lines i-1 / i+1 = N/S, diagonals NW NE SW SE, SECOND unknown first (the reference's pass order,
@@ -69,9 +71,10 @@ tline_prep_kernel(const PrepParams p)
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int j = j0 + ty + 8 * r;
-        const bool st = i < p.pitch0 && j < p.ncols, in = i < p.nrows;
-        float *ln = p.pn + ((long long)b * p.ncols + min(j, p.ncols - 1)) * NC * p.pitch0 + i;
-        float *lt = p.tn + ((long long)b * p.ncols + min(j, p.ncols - 1)) * NUNK * p.pitch0 + i;
+        const bool st = io < p.pitch0 && j < p.ncols, in = i < p.nrows;
+        const long long line0 = ((long long)b * p.S0 + seg0) * p.ncols + min(j, p.ncols - 1);
+        float *ln = p.pn + line0 * NC * p.pitch0 + io;
+        float *lt = p.tn + line0 * NUNK * p.pitch0 + io;
         auto put = [&](int row0, int row1, float v) {
             if (st) ln[(long long)row0 * p.pitch0] = in ? v : 0.f;
             tiles[(row1 * 32 + ty + 8 * r) * 33 + tx] = v;
@@ -89,12 +92,13 @@ tline_prep_kernel(const PrepParams p)
     }
     __syncthreads();
     const int jj = j0 + tx;
-    if (jj < p.pitch1) {
+    const int seg1 = min(jj / p.ns1, p.S1 - 1), jo = jj - seg1 * p.ns1;
+    if (jo < p.pitch1) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const int ii = i0 + ty + 8 * r;
             if (ii < p.nrows) {
-                float *l1 = p.pt + ((long long)b * p.nrows + ii) * NC * p.pitch1 + jj;
+                float *l1 = p.pt + (((long long)b * p.S1 + seg1) * p.nrows + ii) * NC * p.pitch1 + jo;
 #pragma unroll
                 for (int f = 0; f < NC; f++) l1[(long long)f * p.pitch1] = jj < p.ncols ? tiles[(f * 32 + tx) * 33 + ty + 8 * r] : 0.f;
             }
@@ -103,7 +107,7 @@ tline_prep_kernel(const PrepParams p)
 }
 
 // x = T - x0 (late linearisation) or x = T, from the packed T lines back into the caller's dense arrays
-struct FinalParams { float *x[2]; const float *x0[2]; const float *tn; int nunk; int nrows, ncols, pitch0, vec; long long xbs; };
+struct FinalParams { float *x[2]; const float *x0[2]; const float *tn; int nunk; int nrows, ncols, pitch0, vec, S0, ns0; long long xbs; };
 
 static __global__ void __launch_bounds__(256)
 tline_final_kernel(const FinalParams p)
@@ -112,8 +116,9 @@ tline_final_kernel(const FinalParams p)
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= p.nrows) return;
     const long long d = (long long)b * p.xbs + (long long)j * p.nrows + i;
+    const int seg0 = i / p.ns0, io = i - seg0 * p.ns0;
     for (int q = 0; q < p.nunk; q++) {
-        const float *t = p.tn + (((long long)b * p.ncols + j) * p.nunk + q) * p.pitch0 + i;
+        const float *t = p.tn + ((((long long)b * p.S0 + seg0) * p.ncols + j) * p.nunk + q) * p.pitch0 + io;
         if (p.vec) {                                          // 16-byte aligned caller arrays, lines a multiple of 4 long
             float4 v = *reinterpret_cast<const float4 *>(t);
             if (p.x0[q]) {
@@ -143,7 +148,7 @@ static bool tline_geometry(int n, int nunk, int nc, TLGeom &g)
     g.M = 0;
     for (int m : Ms) if (32 * m >= n) { g.M = m; break; }
     if (!g.M || n < 8) return false;
-    const int P = (n + 3) & ~3;
+    const int P = (n + 3) & ~3;                                // n: (longest) segment length
     const size_t room = 227 * 1024;
     static const int eBL = env_int("PDEGPU_TL_BL", 0), eR = env_int("PDEGPU_TL_R", 0), eD = env_int("PDEGPU_TL_D", 0), eK = env_int("PDEGPU_TL_K", 0);
     static const int eNCW = env_int("PDEGPU_TL_NCW", 0);
@@ -163,7 +168,7 @@ static bool tline_geometry(int n, int nunk, int nc, TLGeom &g)
         const int BL = eBL ? eBL : c[0], R = eR ? eR : c[1], D = eD ? eD : c[2];
         if (R % BL || R < 2 * D + BL || (BL != 4 && BL != 8)) continue;
         const int NBR = R / BL + 2;
-        const size_t fixed = (size_t)R * line + 2 * (size_t)((32 * g.M - n + 3) & ~3) * 4 + (size_t)(2 * R) * 8 + (size_t)(2 * NBR + 4) * 4 + 64;
+        const size_t fixed = (size_t)R * line + 2 * (size_t)(32 * g.M - P) * 4 + (size_t)(2 * R) * 8 + (size_t)(2 * NBR + 4) * 4 + 64;
         if (fixed >= room) continue;
         int K = (int)((room - fixed) / (slab + 16 + 32));
         if (K > 8) K = 8;
@@ -208,6 +213,23 @@ int tline_pass(pdegpu_ctx *ctx, TLParams &p, int batch, double bytes, const char
     }
 }
 
+// Lines of more than 800 elements are cut into segments of at most 544 (a multiple of 8 long, so that a block of lines
+// of the other pass never straddles a cut; 544 = 32 lanes x 17: the chunk length with the best measured throughput).
+struct SegPlan { int S, ns, nlast, P; };
+static SegPlan seg_plan(int n)
+{
+    SegPlan s;
+    if (n <= 800) { s.S = 1; s.ns = n; s.nlast = n; }
+    else {
+        s.S = (n + 543) / 544;
+        s.ns = (((n + s.S - 1) / s.S) + 7) & ~7;
+        if ((s.S - 1) * s.ns >= n) s.S = (n + s.ns - 1) / s.ns;
+        s.nlast = n - (s.S - 1) * s.ns;
+    }
+    s.P = (s.ns + 3) & ~3;
+    return s;
+}
+
 template <int FAM>
 int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
@@ -216,17 +238,21 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
     const int nr = sys->nrows, nc = sys->ncols, batch = sys->batch;
     if (iter <= 0) return PDEGPU_OK;
-    if (nr < 8 || nc < 8 || nr > 800 || nc > 800 || batch > 65535) return PDEGPU_ERR_UNSUPPORTED;
+    if (nr < 8 || nc < 8) return PDEGPU_ERR_UNSUPPORTED;
     if (F::PDE && F::EIGHT) return PDEGPU_ERR_UNSUPPORTED;    // NaN-TRACE diagonal of pdeSolvers.c:1179 not restated here
+    const SegPlan s0 = seg_plan(nr), s1 = seg_plan(nc);
+    if (NN == 8 && (s0.S > 1 || s1.S > 1)) return PDEGPU_ERR_UNSUPPORTED;     // diagonal neighbours across a cut: not built
+    if (s0.nlast < 8 || s1.nlast < 8 || (long long)batch * (s0.S > s1.S ? s0.S : s1.S) > 65535) return PDEGPU_ERR_UNSUPPORTED;
     TLGeom g0, g1;
-    if (!tline_geometry(nr, NUNK, NC, g0) || !tline_geometry(nc, NUNK, NC, g1)) return PDEGPU_ERR_UNSUPPORTED;
-    const int pitch0 = (nr + 3) & ~3, pitch1 = (nc + 3) & ~3;
-    const long long S0 = (long long)nc * pitch0, S1 = (long long)nr * pitch1;   // floats per field and problem, column / row pass layout
-    if ((long long)batch * NC * (S0 > S1 ? S0 : S1) >= (1ll << 40)) return PDEGPU_ERR_UNSUPPORTED;
+    if (!tline_geometry(s0.ns, NUNK, NC, g0) || !tline_geometry(s1.ns, NUNK, NC, g1)) return PDEGPU_ERR_UNSUPPORTED;
+    const int pitch0 = s0.P, pitch1 = s1.P;
+    // floats per field and problem: column-pass layout (S0 segments x ncols lines x pitch0), row-pass layout
+    const long long F0 = (long long)s0.S * nc * pitch0, F1 = (long long)s1.S * nr * pitch1;
+    if ((long long)batch * NC * (F0 > F1 ? F0 : F1) >= (1ll << 40)) return PDEGPU_ERR_UNSUPPORTED;
 
     // scratch: packed coefficient lines of both passes, packed T lines of both passes
-    const size_t bytes_pn = (size_t)NC * S0 * batch * 4, bytes_pt = (size_t)NC * S1 * batch * 4;
-    const size_t bytes_tn = (size_t)NUNK * S0 * batch * 4, bytes_tt = (size_t)NUNK * S1 * batch * 4;
+    const size_t bytes_pn = (size_t)NC * F0 * batch * 4, bytes_pt = (size_t)NC * F1 * batch * 4;
+    const size_t bytes_tn = (size_t)NUNK * F0 * batch * 4, bytes_tt = (size_t)NUNK * F1 * batch * 4;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     int rc = pdegpu_scratch_reserve(ctx, up(bytes_pn) + up(bytes_pt) + up(bytes_tn) + up(bytes_tt));
     if (rc) return rc;
@@ -243,11 +269,13 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
         pp.m = sys->m;
         for (int q = 0; q < NUNK; q++) { pp.c[q] = sys->c[q]; pp.d[q] = sys->d[q]; pp.x0[q] = sys->x0[q]; pp.x[q] = sys->x[q]; }
         pp.nrows = nr; pp.ncols = nc; pp.pitch0 = pitch0; pp.pitch1 = pitch1;
+        pp.S0 = s0.S; pp.ns0 = s0.ns; pp.S1 = s1.S; pp.ns1 = s1.ns;
         pp.ibs = sys->batch_stride; pp.pn = PN; pp.pt = PT; pp.tn = TN;
         const size_t smem = (size_t)NC * 32 * 33 * sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
-        dim3 grid((nr + 31) / 32, (nc + 31) / 32, batch);
+        const int ci = nr > s0.S * pitch0 ? nr : s0.S * pitch0, cj = nc > s1.S * pitch1 ? nc : s1.S * pitch1;   // incl. the pads
+        dim3 grid((ci + 31) / 32, (cj + 31) / 32, batch);
         const double fields_in = NN + (NUNK == 2 ? 1 : 0) + NUNK * (F::LATE ? 4 : 3), fields_out = 2 * NC + NUNK;
         PDEGPU_PROF(ctx, "tline_prep_kernel", 4.0 * (fields_in + fields_out) * nr * nc * batch);
         tline_prep_kernel<FAM><<<grid, 256, smem, ctx->stream>>>(pp);
@@ -256,22 +284,25 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 
     TLParams p0, p1;
     memset(&p0, 0, sizeof(p0));
-    p0.coef = PN; p0.tin = TN; p0.tout = TT; p0.obs = (long long)NUNK * S1;
-    p0.pitch = pitch0; p0.opitch = pitch1; p0.q0 = 0; p0.n = nr; p0.nlines = nc; p0.omega = omega;
+    p0.coef = PN; p0.tin = TN; p0.tout = TT;
+    p0.pitch = pitch0; p0.opitch = pitch1; p0.q0 = 0; p0.n = s0.ns; p0.nlines = nc; p0.omega = omega;
+    p0.S = s0.S; p0.ns = s0.ns; p0.nlast = s0.nlast; p0.nfull = nr; p0.oS = s1.S; p0.ons = s1.ns;
     p1 = p0;
-    p1.coef = PT; p1.tin = TT; p1.tout = TN; p1.obs = (long long)NUNK * S0;
-    p1.pitch = pitch1; p1.opitch = pitch0; p1.q0 = NUNK == 2 ? 1 : 0; p1.n = nc; p1.nlines = nr;
+    p1.coef = PT; p1.tin = TT; p1.tout = TN;
+    p1.pitch = pitch1; p1.opitch = pitch0; p1.q0 = NUNK == 2 ? 1 : 0; p1.n = s1.ns; p1.nlines = nr;
+    p1.S = s1.S; p1.ns = s1.ns; p1.nlast = s1.nlast; p1.nfull = nc; p1.oS = s0.S; p1.ons = s0.ns;
 
     const double pass_bytes = sweep_bytes<FAM>() * (double)nr * nc * batch;
     for (int it = 0; it < iter; it++) {
-        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p0, batch, pass_bytes, "tline_pass_kernel<dir0>"))) return rc;
-        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p1, batch, pass_bytes, "tline_pass_kernel<dir1,transposed>"))) return rc;
+        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p0, batch * s0.S, pass_bytes, "tline_pass_kernel<dir0>"))) return rc;
+        if ((rc = tline_pass<NUNK, NN, MODE>(ctx, p1, batch * s1.S, pass_bytes, "tline_pass_kernel<dir1,transposed>"))) return rc;
     }
     {
         FinalParams fp;
         memset(&fp, 0, sizeof(fp));
         for (int q = 0; q < NUNK; q++) { fp.x[q] = sys->x[q]; fp.x0[q] = F::LATE ? sys->x0[q] : nullptr; }
         fp.tn = TN; fp.nunk = NUNK; fp.nrows = nr; fp.ncols = nc; fp.pitch0 = pitch0; fp.xbs = sys->batch_stride;
+        fp.S0 = s0.S; fp.ns0 = s0.ns;
         bool vec = (nr % 4 == 0) && (sys->batch_stride % 4 == 0);
         for (int q = 0; q < NUNK; q++) vec = vec && (((uintptr_t)sys->x[q] | (uintptr_t)(F::LATE ? sys->x0[q] : nullptr)) & 15) == 0;
         fp.vec = vec ? 1 : 0;

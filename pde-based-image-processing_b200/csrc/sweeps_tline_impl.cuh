@@ -88,7 +88,7 @@ tline_pass_kernel(const TLParams p)
     float *ring = smem;
     // 32M - n floats of padding (rounded to 16 bytes) after the ring and after the slabs: lanes past the end of a line read them
     constexpr int PADF = 32 * M;
-    const int pad = (PADF - p.n + 3) & ~3;
+    const int pad = PADF - P;
     float *slabs = ring + (size_t)R * SP + pad;
     uint64_t *bars = reinterpret_cast<uint64_t *>(slabs + (size_t)K * NC * P + pad);
     uint64_t *full = bars, *empty = bars + K, *rfull = bars + 2 * K, *solved = bars + 2 * K + R;
@@ -109,7 +109,7 @@ tline_pass_kernel(const TLParams p)
     }
     __syncthreads();
 
-    const int n = p.n, nlines = p.nlines;
+    const int nlines = p.nlines;
     const int B0 = (int)((long long)blockIdx.x * p.TB / gridDim.x), B1 = (int)((long long)(blockIdx.x + 1) * p.TB / gridDim.x);
     const int nblk = B1 - B0;
     const bool redundant = B1 < p.TB && (B1 % p.NB) != 0;
@@ -137,7 +137,20 @@ tline_pass_kernel(const TLParams p)
                 if (lane == 0) mbar_arrive(&empty[slot]);
                 break;
             }
-            const int flags = d0.y, img = d0.z;
+            const int flags = d0.y, pi = d0.z;                 // pi = problem of the pass = image * S + segment
+            const int seg = flags >> 16;
+            const int n = seg == p.S - 1 ? p.nlast : p.ns;
+            const bool cutL = seg > 0, cutR = seg < p.S - 1;
+            // values across the cuts, from the start of the pass (global memory; used after the row formulas)
+            float hL0 = 0.f, hL1 = 0.f, hR0 = 0.f, hR1 = 0.f;
+            if (lane == 0 && (cutL || cutR)) {
+                const long long ls = (long long)NUNK * P;
+                const float *tl = p.tin + ((long long)(pi - 1) * nlines + d0.w) * ls + (p.ns - 1);
+                const float *tr = p.tin + ((long long)(pi + 1) * nlines + d0.w) * ls;
+                const int u0 = (NUNK == 2 ? p.q0 : 0) * P, u1 = (NUNK == 2 ? (p.q0 ^ 1) : 0) * P;
+                if (cutL) { hL0 = tl[u0]; if (NUNK == 2) hL1 = tl[u1]; }
+                if (cutR) { hR0 = tr[u0]; if (NUNK == 2) hR1 = tr[u1]; }
+            }
             const bool odd = flags & 1, eLo = flags & 2, eHi = flags & 4, owned = flags & 8, relaxed = !(flags & 16);
             const int gh = l + BL + 1;
             // ring slots g % R, (g -+ 1) % R and their use counts g / R, (g -+ 1) / R (g = l + BL)
@@ -171,8 +184,9 @@ tline_pass_kernel(const TLParams p)
                 // is padded so that lanes past the end of a short line read (and discard) whatever follows.
                 {
                     float *sw_ = const_cast<float *>(sl);
-                    if (lane == 0) {
-                        sw_[rWP * P] = 0.f; sw_[rWN * P + n - 1] = 0.f;
+                    if (lane == 0) {                          // (at a cut the neighbour exists: see below)
+                        if (!cutL) sw_[rWP * P] = 0.f;
+                        if (!cutR) sw_[rWN * P + n - 1] = 0.f;
                         if (NN == 8) { sw_[(rDG + 0) * P] = 0.f; sw_[(rDG + 2) * P] = 0.f; sw_[(rDG + 1) * P + n - 1] = 0.f; sw_[(rDG + 3) * P + n - 1] = 0.f; }
                     }
                     if (!eLo || !eHi) {
@@ -232,6 +246,24 @@ tline_pass_kernel(const TLParams p)
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[slot]);     // rows are in registers: the slab can be refilled
+                if (cutL || cutR) {
+                    // ends of a segment that are not ends of the line: the weight stays in the diagonal, the neighbour's
+                    // value (start of the pass) goes to the right-hand side, the row is cut off from the recurrence
+                    hR0 = __shfl_sync(FULLMASK, hR0, 0); hR1 = __shfl_sync(FULLMASK, hR1, 0);
+                    if (cutL && lane == 0) {
+                        d[0] -= a[0] * hL0; a[0] = 0.f;
+                        if (NUNK == 2) { ds[0] -= as[0] * hL1; as[0] = 0.f; }
+                    }
+                    if (cutR) {
+#pragma unroll
+                        for (int k = 0; k < M; k++)
+                            if (o + k == n - 1) {
+                                d[k] -= c[k] * hR0;
+                                if (NUNK == 2) ds[k] -= c[k] * hR1;
+                                c[k] = 0.f;
+                            }
+                    }
+                }
                 TLP(3);
 #pragma unroll 1
                 for (int q = 0; q < NUNK; q++) {
@@ -262,16 +294,20 @@ tline_pass_kernel(const TLParams p)
             }
             done = __shfl_sync(FULLMASK, done, 0);
             TLP(7);
-            const int cnt = flags >> 8;
+            const int cnt = (flags >> 8) & 0xff;
             if (owned && (int)done == cnt) {
                 // this warp completed block lb: write its lines to T_out (transposed: the packed T lines of the next pass)
                 __threadfence_block();
                 const int j0 = d1.x;
                 const float *rblk = ring + (size_t)(((lb + 1) * BL) % R) * SP;
                 const long long ostep = (long long)NUNK * p.opitch;               // floats between consecutive elements of a line
+                // element k of this segment is line seg*ns + k of the other direction; lines j0.. are elements of its
+                // segment j0 / ons (a block never straddles two: ons is a multiple of BL)
+                const int img = pi / p.S, oseg = j0 / p.ons;
+                float *obase = p.tout + (((long long)img * p.oS + oseg) * p.nfull + (long long)seg * p.ns) * ostep + (j0 - oseg * p.ons);
 #pragma unroll 1
                 for (int qq = 0; qq < NUNK; qq++) {
-                    float *out = p.tout + (long long)img * p.obs + (long long)qq * p.opitch + j0;
+                    float *out = obase + (long long)qq * p.opitch;
                     const float *rq = rblk + qq * P;
                     if (cnt == BL && BL == 8) {
                         // half-warp h writes lines 4h..4h+3 of 16 consecutive elements: full 32-byte sectors
@@ -340,7 +376,7 @@ tline_pass_kernel(const TLParams p)
                     TLP_COUNT(6);
                     int *dsc = desc + slot * 8;
                     *reinterpret_cast<int4 *>(dsc) = make_int4(l, (odd ? 1 : 0) | (j > 0 ? 2 : 0) | (j + 1 < nlines ? 4 : 0) | (lp.lb < nblk ? 8 : 0)
-                                                                  | (noupdate ? 16 : 0) | (cnt << 8), lp.img, j);
+                                                                  | (noupdate ? 16 : 0) | (cnt << 8) | ((lp.img % p.S) << 16), lp.img, j);
                     *reinterpret_cast<int4 *>(dsc + 4) = make_int4(j0, lp.lb, rsl, (int)usl);
                     if (noupdate) mbar_arrive(&full[slot]);
                     else {

@@ -254,11 +254,9 @@ static bool win_geometry(int n, int nunk, WinGeom &g)
 template <int FAM, int DIR, int M>
 int launch_window(pdegpu_ctx *ctx, const WinParams &p, const WinGeom &g, int batch)
 {
-    static bool attr_set[16] = {false};
-    if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_window_kernel<FAM, DIR, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window_kernel)");
-        attr_set[ctx->device & 15] = true;
+    {   // every launch: the attribute is per device and the call is cheap (no static per-ordinal bookkeeping)
+    cudaError_t e = cudaFuncSetAttribute(alr_window_kernel<FAM, DIR, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window_kernel)");
     }
     const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_window_kernel<dir0>" : "alr_window_kernel<dir1,transposed>",

@@ -296,11 +296,9 @@ alr_window2_kernel(const WinParams p)
 template <int FAM, int DIR, int M, int VW, bool AL>
 int launch_window2(pdegpu_ctx *ctx, const WinParams &p, size_t smem, int batch)
 {
-    static bool attr_set[16] = {false};
-    if (!attr_set[ctx->device & 15]) {
-        cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M, VW, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window2_kernel)");
-        attr_set[ctx->device & 15] = true;
+    {   // every launch: the attribute is per device and the call is cheap (no static per-ordinal bookkeeping)
+    cudaError_t e = cudaFuncSetAttribute(alr_window2_kernel<FAM, DIR, M, VW, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(alr_window2_kernel)");
     }
     const int grid = p.TB < ctx->sm_count ? p.TB : ctx->sm_count;
     PDEGPU_PROF(ctx, DIR == 0 ? "alr_window2_kernel<dir0>" : "alr_window2_kernel<dir1,transposed>",

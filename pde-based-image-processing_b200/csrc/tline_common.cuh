@@ -32,11 +32,15 @@ enum { TL_WP = 0, TL_WN = 1, TL_WL = 2, TL_WH = 3, TL_C0 = 4, TL_D0 = 5,
 struct TLParams {
     const float *coef;             // packed coefficient lines of this direction
     const float *tin;              // packed T lines (physical order U, V)
-    float       *tout;             // T out = packed T lines of the OTHER direction: element k of line j of unknown q of
-    long long    obs;              //   problem b at b*obs + (k*NUNK + q)*opitch + j
+    float       *tout;             // T out = packed T lines of the OTHER direction (element k of line j -> element j of line k)
     int pitch, opitch, SP;         // floats between fields of a packed line (in / out); floats between ring entries
     int q0;                        // flow families: physical index (0 = U, 1 = V) of the unknown this pass solves first
-    int n, nlines;                 // line length, lines per problem
+    int n, nlines;                 // (longest) segment length, lines per problem
+    // LONG LINES are cut into S segments of ns elements (the last one nlast): segment s of every line of problem b is
+    // "problem" b*S + s of the pass, stored as such by the preparation kernel, and exact within itself. Across a cut the
+    // neighbour's value is taken from the START of the pass (block Jacobi between segments: same fixed point). oS / ons:
+    // the same for the other direction, whose layout this pass writes.
+    int S, ns, nlast, nfull, oS, ons;
     int NB, TB;                    // blocks of BL lines per problem / in total
     int BL;                        // lines per output block (4 or 8)
     int R, D, K, NBR, NCW;         // ring lines, lead of the even lines in pairs, coefficient slabs, block slots, consumer warps

@@ -29,6 +29,7 @@ ap.add_argument("--omega", type=float, default=1.9)
 ap.add_argument("--solver", type=int, default=2)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--resid", action="store_true", help="flow families: reference-defined residual norm before / after the call")
 ap.add_argument("--tag", default="")
 a = ap.parse_args()
 
@@ -98,6 +99,20 @@ if a.check:
     out["check_rel_err_vs_gen0"] = errs
     out["finite"] = bool(all(np.isfinite(q).all() for q in res[1]))
     ctx.set_kernel_path(1)
+
+if a.resid and a.fam in ("elin4", "llin4"):
+    def resnorm(xs):
+        RU = torch.empty(B * n, device=dev); RV = torch.empty(B * n, device=dev)
+        ctx.residual(mk(xs), 1, RU.data_ptr(), RV.data_ptr())
+        ctx.sync()
+        return float(torch.sqrt(torch.nanmean(RU.double() ** 2 + RV.double() ** 2)))
+    xs = [t.clone() for t in init]
+    r = [resnorm(xs)]
+    for _ in range(3):
+        ctx.relax(mk(xs), a.iter, a.omega, a.solver)
+        ctx.sync()
+        r.append(resnorm(xs))
+    out["residual_norms_per_call"] = r
 
 x = [t.clone() for t in init]
 sysd = mk(x)
