@@ -189,6 +189,19 @@ def cpu_reference_throughput(seconds_target=10.0, calls_per_worker=None):
                       f"= {units:.0f} Mpix*iter in {dt:.1f} s; single-thread rate {NROWS * NCOLS * ITER / 1e6 / one:.2f} {UNIT}"}, dt
 
 
+def workload_config(B, solver, kernels, world):
+    """the SAME description for both arms: what is solved is identical (shape, iter, omega, solver); how many systems are
+    in flight at once is an implementation detail of each arm and is stated in cpu_baseline.sample / batch_per_gpu"""
+    n = NROWS * NCOLS
+    return {"workload": f"configs[1]: Oflow_sor_llin4_2d inner solve of the 640x480 late-linearisation flow; "
+                        f"independent 480x640 systems, iter={ITER}, omega={OMEGA}, solver={solver} "
+                        f"({'line relaxation' if solver == 2 else 'point SOR'})",
+            "nrows": NROWS, "ncols": NCOLS, "iter": ITER, "omega": OMEGA, "solver": solver,
+            "batch_per_gpu": B, "kernels": kernels,
+            "l2": f"inputs larger than L2: {13 * B * n * 4 / 1e6:.0f} MB of fields per pass vs 126 MB L2",
+            "parallelism": f"batch-parallel x{world}, no data-path collective"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -210,8 +223,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: Oflow_sor_llin4_2d inner solve, 480x640 systems, ALR iter=4 omega=1.9 "
-                               "(reference CPU code, one worker per host core)"},
+        "config": workload_config(args.batch, args.solver, "stream", args.gpus),
         "cpu_baseline": r,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -741,13 +753,7 @@ def run_ours(args):
             "metric": metric_name(args.solver), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: Oflow_sor_llin4_2d inner solve of the 640x480 late-linearisation flow; "
-                                   f"batch of {B} independent 480x640 systems per GPU, iter={ITER}, omega={OMEGA}, solver={args.solver} "
-                                   f"({'zebra line relaxation' if args.solver == 2 else 'red-black point SOR'})",
-                       "batch_per_gpu": B, "nrows": NROWS, "ncols": NCOLS, "iter": ITER, "omega": OMEGA, "solver": args.solver,
-                       "kernels": args.kernels,
-                       "l2": f"inputs larger than L2: {13 * B * n * 4 / 1e6:.0f} MB of fields per pass vs 126 MB L2",
-                       "parallelism": f"batch-parallel x{world}, no data-path collective"},
+            "config": workload_config(B, args.solver, args.kernels, world),
             "e2e": {"value": e2e_val, "unit": UNIT,
                     "h2d_bytes_per_step": 13 * n * 4 * args.e2e_calls, "d2h_bytes_per_step": 2 * n * 4 * args.e2e_calls,
                     "calls_per_step": args.e2e_calls, "api": "pdegpu_oflow_sor_llin4_2d (host pointers, pinned)"},

@@ -77,6 +77,21 @@ int         pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen);
 /* Kernel generation: 0 = "simple" global-memory kernels (kept as an in-library cross-check),
  * 1 = streaming register/shared-memory kernels (default). */
 int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);
+/* Order in which solver 2 (alternating line relaxation) visits the lines of a direction.
+ *   PDEGPU_ORDER_FAST (default): zebra -- even lines, then odd lines; every line of a colour in parallel. Same fixed
+ *     point as the reference, the HBM-bound kernel of the throughput numbers; its iterate after a FEW sweeps differs
+ *     from the reference's (information travels two lines per sweep instead of across the image).
+ *   PDEGPU_ORDER_REFERENCE: the reference's own order -- line j sees the new line j-1 and the old line j+1
+ *     (GS_ALR_SOR_*: opticalflowSolvers.c:196,690,1677; disparitySolvers.c:154; pdeSolvers.c:277,344). Iterates agree
+ *     with the reference sweep by sweep (fp32 rounding apart), so the unchanged .m drivers give the reference's flow at
+ *     the reference's iteration counts. Serial from line to line: the parallelism is the batch (one CTA per problem)
+ *     and the lanes inside a line. Also selected by the environment variable PDEGPU_ORDER=reference (for callers that
+ *     never see the context: the MEX gateways).
+ * Solver 1 (point relaxation) is not affected. Applies to pdegpu_dev_relax and everything built on it. */
+#define PDEGPU_ORDER_FAST      0
+#define PDEGPU_ORDER_REFERENCE 1
+int         pdegpu_set_sweep_order(pdegpu_ctx *ctx, int order);
+int         pdegpu_get_sweep_order(const pdegpu_ctx *ctx);
 
 /* Device / pinned memory owned by the library (for the pdegpu_dev_* entry points). */
 int         pdegpu_malloc(pdegpu_ctx *ctx, void **dptr, size_t bytes);

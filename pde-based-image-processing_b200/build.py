@@ -99,9 +99,22 @@ def build_gateways(force=False):
     return MEXLIB
 
 
+def build_cli(force=False):
+    """pdegpu_flow_batch: the batch command-line front end (plain C on the C ABI)."""
+    src = os.path.join(HERE, "cli", "pdegpu_flow_batch.c")
+    exe = os.path.join(HERE, "cli", "pdegpu_flow_batch")
+    if not os.path.exists(src):
+        return None
+    if force or not _newer(exe, [src, LIB, os.path.join(HERE, "..", "include", "pdegpu.h")]):
+        _run(["gcc", "-O2", "-Wall", "-Wextra", "-I" + os.path.join(HERE, "..", "include"), src, "-L" + HERE, "-lpdegpu",
+              "-Wl,-rpath,$ORIGIN/..", "-o", exe])
+    return exe
+
+
 def build_all(force=False, verbose=False):
     lib = build_lib(force, verbose)
     mex = build_gateways(force)
+    build_cli(force)
     return lib, mex
 
 

@@ -55,6 +55,8 @@ extern "C" int pdegpu_init(int device, pdegpu_ctx **out)
     ctx->kernel_path = 1;
     const char *env = getenv("PDEGPU_KERNELS");
     if (env && strcmp(env, "simple") == 0) ctx->kernel_path = 0;
+    env = getenv("PDEGPU_ORDER");
+    if (env && strcmp(env, "reference") == 0) ctx->sweep_order = PDEGPU_ORDER_REFERENCE;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { free(ctx); return pdegpu_check_cuda(nullptr, e, "cudaStreamCreate"); }
     *out = ctx;
@@ -239,6 +241,16 @@ extern "C" int pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path)
     ctx->kernel_path = path;
     return PDEGPU_OK;
 }
+
+extern "C" int pdegpu_set_sweep_order(pdegpu_ctx *ctx, int order)
+{
+    if (!ctx || (order != PDEGPU_ORDER_FAST && order != PDEGPU_ORDER_REFERENCE)) return PDEGPU_ERR_ARG;
+    if (ctx->sweep_order != order) ctx->graph_epoch++;     // captured graphs hold the other order's kernels
+    ctx->sweep_order = order;
+    return PDEGPU_OK;
+}
+
+extern "C" int pdegpu_get_sweep_order(const pdegpu_ctx *ctx) { return ctx ? ctx->sweep_order : PDEGPU_ERR_ARG; }
 
 // ---------------------------------------------------------------------------------------------
 int pdegpu_arena_reserve(pdegpu_ctx *ctx, size_t bytes)

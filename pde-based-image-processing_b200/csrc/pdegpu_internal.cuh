@@ -25,6 +25,7 @@ struct pdegpu_ctx {
     size_t        scratch_bytes;
     unsigned long long launches;
     int           kernel_path;     // 0 simple, 1 streaming
+    int           sweep_order;     // PDEGPU_ORDER_FAST / PDEGPU_ORDER_REFERENCE (solver 2)
     // optional per-launch timing (pdegpu_profile_*): one CUDA event pair per kernel launch
     int           prof_on;
     int           prof_n, prof_cap;
@@ -131,6 +132,7 @@ template <int FAM> constexpr double sweep_bytes()
 // Kernel launchers implemented in the .cu files (all asynchronous on ctx->stream)
 // ------------------------------------------------------------------------------------------
 int relax_simple(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);
+int relax_lexline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega);                // solver 2 in the reference's line order (sweeps_tline.cu)
 int relax_stream(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);   // returns PDEGPU_ERR_UNSUPPORTED when it has no kernel for the case
 
 int op_residual(pdegpu_ctx *ctx, const pdegpu_system *sys, int nframes, float *RU, float *RV, bool lhs);

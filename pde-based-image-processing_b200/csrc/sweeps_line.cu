@@ -543,15 +543,17 @@ int alr_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     }
     SysView vt = make_view(&tsys);
     for (int it = 0; it < iter; it++) {
-        for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 0>(ctx, v, sys, colour, omega))) return rc;
+        // interior-only lines (8-neighbour PDE) start at line 1: colour 1 there = the even lines, relaxed first as everywhere
+        constexpr int cflip = (F::PDE && F::EIGHT) ? 1 : 0;
+        for (int cc = 0; cc < 2; cc++) if ((rc = alr_pass<FAM, 0>(ctx, v, sys, cc ^ cflip, omega))) return rc;
         if (xpose) {
             for (int q = 0; q < F::NUNK; q++)
                 if ((rc = transpose_fields(ctx, xT[q], sys->x[q], sys->nrows, sys->ncols, sys->batch, sys->batch_stride, npix))) return rc;
-            for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 2>(ctx, vt, &tsys, colour, omega))) return rc;
+            for (int cc = 0; cc < 2; cc++) if ((rc = alr_pass<FAM, 2>(ctx, vt, &tsys, cc ^ cflip, omega))) return rc;
             for (int q = 0; q < F::NUNK; q++)
                 if ((rc = transpose_fields(ctx, sys->x[q], xT[q], sys->ncols, sys->nrows, sys->batch, npix, sys->batch_stride))) return rc;
         } else {
-            for (int colour = 0; colour < 2; colour++) if ((rc = alr_pass<FAM, 1>(ctx, v, sys, colour, omega))) return rc;
+            for (int cc = 0; cc < 2; cc++) if ((rc = alr_pass<FAM, 1>(ctx, v, sys, cc ^ cflip, omega))) return rc;
         }
     }
     return PDEGPU_OK;

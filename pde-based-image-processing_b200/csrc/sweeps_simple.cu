@@ -158,13 +158,15 @@ static int run_line(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     constexpr int NUNK = Fam<FAM>::NUNK;
     if (Fam<FAM>::PDE && Fam<FAM>::EIGHT) iter = 1;            // pdeSolvers.c:362
     int rc;
+    // interior-only lines (8-neighbour PDE) start at line 1: colour 1 there = the even lines, relaxed first as everywhere
+    constexpr int cflip = (Fam<FAM>::PDE && Fam<FAM>::EIGHT) ? 1 : 0;
     for (int it = 0; it < iter; it++) {
-        for (int colour = 0; colour < 2; colour++)
+        for (int cc = 0; cc < 2; cc++)
             for (int q = 0; q < NUNK; q++)
-                if ((rc = run_line_pass<FAM, 0>(ctx, v, sys, colour, q, omega))) return rc;
-        for (int colour = 0; colour < 2; colour++)
+                if ((rc = run_line_pass<FAM, 0>(ctx, v, sys, cc ^ cflip, q, omega))) return rc;
+        for (int cc = 0; cc < 2; cc++)
             for (int q = NUNK - 1; q >= 0; q--)
-                if ((rc = run_line_pass<FAM, 1>(ctx, v, sys, colour, q, omega))) return rc;
+                if ((rc = run_line_pass<FAM, 1>(ctx, v, sys, cc ^ cflip, q, omega))) return rc;
     }
     return PDEGPU_OK;
 }

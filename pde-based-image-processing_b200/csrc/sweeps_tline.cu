@@ -4,6 +4,7 @@
 // GS_ALR_SOR_elin4_2d / _llin4_2d / _llin8_2d (opticalflowSolvers.c:196,690,1677), the disparity
 // GS_ALR_SOR_llin4_2d (disparitySolvers.c:154) and GS_ALR_SOR_4_2d (pdeSolvers.c:277).
 #include "sweeps_tline_impl.cuh"
+#include "sweeps_lex_impl.cuh"
 #include <cstdlib>
 
 namespace {
@@ -237,11 +238,10 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, MODE = F::PDE ? 1 : 0;
     constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
     const int nr = sys->nrows, nc = sys->ncols, batch = sys->batch;
+    if (F::PDE && F::EIGHT) iter = 1;                         // pdeSolvers.c:362: whatever the caller asks for
     if (iter <= 0) return PDEGPU_OK;
     if (nr < 8 || nc < 8) return PDEGPU_ERR_UNSUPPORTED;
-    if (F::PDE && F::EIGHT) return PDEGPU_ERR_UNSUPPORTED;    // NaN-TRACE diagonal of pdeSolvers.c:1179 not restated here
     const SegPlan s0 = seg_plan(nr), s1 = seg_plan(nc);
-    if (NN == 8 && (s0.S > 1 || s1.S > 1)) return PDEGPU_ERR_UNSUPPORTED;     // diagonal neighbours across a cut: not built
     if (s0.nlast < 8 || s1.nlast < 8 || (long long)batch * (s0.S > s1.S ? s0.S : s1.S) > 65535) return PDEGPU_ERR_UNSUPPORTED;
     TLGeom g0, g1;
     if (!tline_geometry(s0.ns, NUNK, NC, g0) || !tline_geometry(s1.ns, NUNK, NC, g1)) return PDEGPU_ERR_UNSUPPORTED;
@@ -286,10 +286,11 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     memset(&p0, 0, sizeof(p0));
     p0.coef = PN; p0.tin = TN; p0.tout = TT;
     p0.pitch = pitch0; p0.opitch = pitch1; p0.q0 = 0; p0.n = s0.ns; p0.nlines = nc; p0.omega = omega;
+    p0.skip_border = (F::PDE && F::EIGHT) ? 1 : 0;               // pdeSolvers.c:1155,1290: the outermost lines are not relaxed
     p0.S = s0.S; p0.ns = s0.ns; p0.nlast = s0.nlast; p0.nfull = nr; p0.oS = s1.S; p0.ons = s1.ns;
     p1 = p0;
     p1.coef = PT; p1.tin = TT; p1.tout = TN;
-    p1.pitch = pitch1; p1.opitch = pitch0; p1.q0 = NUNK == 2 ? 1 : 0; p1.n = s1.ns; p1.nlines = nr;
+    p1.pitch = pitch1; p1.opitch = pitch0; p1.q0 = 1; p1.n = s1.ns; p1.nlines = nr;   // (q0: scalar families only read it as "row pass")
     p1.S = s1.S; p1.ns = s1.ns; p1.nlast = s1.nlast; p1.nfull = nc; p1.oS = s0.S; p1.ons = s0.ns;
 
     const double pass_bytes = sweep_bytes<FAM>() * (double)nr * nc * batch;
@@ -314,6 +315,278 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
     return PDEGPU_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// SMALL PROBLEMS (the coarse levels of every pyramid / multigrid cycle): the WHOLE relax call in one launch, one CTA per
+// problem, every field resident in shared memory from the first load to the last store (north_star subsystem 4).
+// The persistent pass kernel above needs 10 launches per call (preparation, 2 x iter passes, recovery of the increment),
+// each of which is pure launch + drain latency on a 37 x 49 level; here the total-field conversion happens on the way
+// into shared memory, the sweeps (same zebra order, same row formulas, same partitioned Thomas solve: one warp per line)
+// run between __syncthreads, and the increment is formed on the way out.
+// Lines along j are strided in shared memory: an odd pitch keeps the lanes' chunks (M odd) on different banks.
+// ------------------------------------------------------------------------------------------------------------------
+struct SmallParams {
+    float *x[2];
+    const float *x0[2], *m, *c[2], *d[2], *w[4];
+    int nr, nc, pitch, iter;
+    long long bs;
+    float omega;
+};
+
+constexpr int kSmallThreads = 512;
+
+template <int FAM, int M>
+__global__ void __launch_bounds__(kSmallThreads, 1)
+tline_small_kernel(const SmallParams p)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK;
+    constexpr bool PDE = F::PDE;
+    extern __shared__ float sm[];
+    const int nr = p.nr, nc = p.nc, P = p.pitch;
+    const int FS = P * nc;                                    // floats per field
+    float *W = sm;                                            // wW, wN, wE, wS
+    float *MM = W + 4 * FS;                                   // (flow families)
+    float *C = MM + (NUNK == 2 ? FS : 0), *D = C + NUNK * FS, *T = D + NUNK * FS;
+    const long long base = (long long)blockIdx.x * p.bs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = kSmallThreads / 32;
+    for (int idx = threadIdx.x; idx < nr * nc; idx += kSmallThreads) {
+        const int j = idx / nr, i = idx - j * nr, dst = j * P + i;
+        const long long src = base + idx;
+#pragma unroll
+        for (int k = 0; k < 4; k++) W[k * FS + dst] = p.w[k][src];
+        const float mm = NUNK == 2 ? p.m[src] : 0.f;
+        if (NUNK == 2) MM[dst] = mm;
+        float x0[NUNK];
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) x0[q] = F::LATE ? p.x0[q][src] : 0.f;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) {
+            const float dd = p.d[q][src];
+            D[q * FS + dst] = dd;
+            C[q * FS + dst] = tl_cprime(p.c[q][src], dd, mm, x0[q], x0[NUNK - 1 - q], F::LATE, NUNK == 2);
+            T[q * FS + dst] = x0[q] + p.x[q][src];
+        }
+    }
+    __syncthreads();
+    const float omega = p.omega, om1 = 1.0f - p.omega;
+    const int o = lane * M;
+    for (int it = 0; it < p.iter; it++) {
+#pragma unroll 1
+        for (int dir = 0; dir < 2; dir++) {
+            const int n = dir == 0 ? nr : nc, nl = dir == 0 ? nc : nr;
+            const int es = dir == 0 ? 1 : P, ls = dir == 0 ? P : 1;      // element / line strides
+            // roles (tline_common.cuh): column pass previous/next = N/S, lines -/+ = W/E; row pass W/E and N/S
+            const float *Wp = W + (dir == 0 ? W_N : W_W) * FS, *Wn = W + (dir == 0 ? W_S : W_E) * FS;
+            const float *Wl = W + (dir == 0 ? W_W : W_N) * FS, *Wh = W + (dir == 0 ? W_E : W_S) * FS;
+#pragma unroll 1
+            for (int colour = 0; colour < 2; colour++) {
+#pragma unroll 1
+                for (int l = colour + 2 * warp; l < nl; l += 2 * nwarps) {
+                    const bool eLo = l > 0, eHi = l < nl - 1;
+#pragma unroll 1
+                    for (int qq = 0; qq < NUNK; qq++) {
+                        const int q = (NUNK == 2 && dir == 1) ? 1 - qq : qq;           // row pass: second unknown first
+                        float *Tq = T + q * FS;
+                        const float *To = T + (NUNK - 1 - q) * FS, *Cq = C + q * FS, *Dq = D + q * FS;
+                        float a[M], b[M], c[M], d[M];
+#pragma unroll
+                        for (int k = 0; k < M; k++) {
+                            const int e = o + k, ec = min(e, n - 1);
+                            const bool ok = e < n;
+                            const int ix = l * ls + ec * es;
+                            const float wp = e > 0 ? Wp[ix] : 0.f, wn = e < n - 1 ? Wn[ix] : 0.f;
+                            const float wl = eLo ? Wl[ix] : 0.f, wh = eHi ? Wh[ix] : 0.f;
+                            const float sw = (wl + wh) + (wp + wn);
+                            const float cr = (eLo ? wl * Tq[ix - ls] : 0.f) + (eHi ? wh * Tq[ix + ls] : 0.f);
+                            const float Cc = Cq[ix], Dd = Dq[ix];
+                            float bb, dd;
+                            if (PDE) {
+                                const bool has = !is_nan(Dd);
+                                bb = has ? Dd : sw; dd = has ? cr + Cc : cr;
+                            } else {
+                                const bool has = !is_nan(Cc);
+                                bb = has ? sw + Dd : sw;
+                                float t = Cc;
+                                if (NUNK == 2) t -= MM[ix] * To[ix];
+                                dd = has ? cr + t : cr;
+                            }
+                            a[k] = ok ? -wp : 0.f; c[k] = ok ? -wn : 0.f; b[k] = ok ? bb : 1.0f; d[k] = ok ? dd : 0.f;
+                        }
+                        chunk_solve<M>(a, c, b, d, lane);
+#pragma unroll
+                        for (int k = 0; k < M; k++) {
+                            const int e = o + k;
+                            if (e < n) { const int ix = l * ls + e * es; Tq[ix] = omega * d[k] + om1 * Tq[ix]; }
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int idx = threadIdx.x; idx < nr * nc; idx += kSmallThreads) {
+        const int j = idx / nr, i = idx - j * nr, src = j * P + i;
+        const long long dst = base + idx;
+#pragma unroll
+        for (int q = 0; q < NUNK; q++) p.x[q][dst] = F::LATE ? T[q * FS + src] - p.x0[q][dst] : T[q * FS + src];
+    }
+}
+
+template <int FAM>
+int tline_small_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    using F = Fam<FAM>;
+    if (F::EIGHT) return PDEGPU_ERR_UNSUPPORTED;
+    static const int enabled = env_int("PDEGPU_TL_SMALL", 1);
+    if (!enabled || iter <= 0) return PDEGPU_ERR_UNSUPPORTED;
+    const int nr = sys->nrows, nc = sys->ncols, nmax = nr > nc ? nr : nc;
+    if (nr < 3 || nc < 3 || nmax > 288) return PDEGPU_ERR_UNSUPPORTED;
+    const int pitch = nr | 1;
+    const int nf = 4 + (F::NUNK == 2 ? 1 : 0) + 3 * F::NUNK;
+    const size_t smem = (size_t)nf * pitch * nc * sizeof(float);
+    if (smem > 227 * 1024) return PDEGPU_ERR_UNSUPPORTED;
+    SmallParams sp;
+    memset(&sp, 0, sizeof(sp));
+    for (int q = 0; q < F::NUNK; q++) { sp.x[q] = sys->x[q]; sp.x0[q] = sys->x0[q]; sp.c[q] = sys->c[q]; sp.d[q] = sys->d[q]; }
+    sp.m = sys->m;
+    for (int k = 0; k < 4; k++) sp.w[k] = sys->w[k];
+    sp.nr = nr; sp.nc = nc; sp.pitch = pitch; sp.iter = iter; sp.bs = sys->batch_stride; sp.omega = omega;
+    const double bytes = sweep_bytes<FAM>() * 2.0 * iter * nr * nc * sys->batch;
+    cudaError_t e;
+    if (nmax <= 160) {
+        e = cudaFuncSetAttribute(tline_small_kernel<FAM, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_small_kernel)");
+        PDEGPU_PROF(ctx, "tline_small_kernel", bytes);
+        tline_small_kernel<FAM, 5><<<sys->batch, kSmallThreads, smem, ctx->stream>>>(sp);
+    } else {
+        e = cudaFuncSetAttribute(tline_small_kernel<FAM, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_small_kernel)");
+        PDEGPU_PROF(ctx, "tline_small_kernel", bytes);
+        tline_small_kernel<FAM, 9><<<sys->batch, kSmallThreads, smem, ctx->stream>>>(sp);
+    }
+    PDEGPU_LAUNCH_CHECK(ctx, "tline_small_kernel");
+    return PDEGPU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// REFERENCE ORDER (sweeps_lex_impl.cuh): the same total-field formulation and packed lines, whole lines (no segments),
+// relaxed one after the other as the reference does. Sequence per call: preparation, then per iteration the column
+// pass in place on the column-layout T lines, their transposition, the row pass in place, the transposition back; the
+// increment is recovered as in the zebra path.
+// ------------------------------------------------------------------------------------------------------------------
+struct LexGeom { int Mr, KS, RL; size_t smem; };
+
+static bool lex_geometry(int n, int nunk, int nc, LexGeom &g)
+{
+    const int P = (n + 3) & ~3;
+    g.Mr = ((n + 31) / 32) | 1;
+    const size_t room = 227 * 1024;
+    const size_t slab = (size_t)nc * P * 4, line = (size_t)nunk * P * 4, scratch = (size_t)3 * 32 * g.Mr * 4;
+    const int cand[][2] = {{2, 4}, {2, 3}, {1, 4}, {1, 3}};
+    for (auto &c : cand) {
+        const size_t need = c[0] * slab + c[1] * line + scratch + (size_t)(2 * c[0] + 2 * c[1]) * 8 + 128;
+        if (need <= room) { g.KS = c[0]; g.RL = c[1]; g.smem = need; return true; }
+    }
+    return false;
+}
+
+template <int NUNK, int NN, int MODE>
+int lex_pass(pdegpu_ctx *ctx, LexParams &p, int batch, double bytes, const char *name)
+{
+    constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
+    LexGeom g;
+    if (!lex_geometry(p.n, NUNK, NC, g)) return PDEGPU_ERR_UNSUPPORTED;
+    p.Mr = g.Mr; p.KS = g.KS; p.RL = g.RL;
+    cudaError_t e = cudaFuncSetAttribute(lex_pass_kernel<NUNK, NN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(lex_pass_kernel)");
+    PDEGPU_PROF(ctx, name, bytes);
+    lex_pass_kernel<NUNK, NN, MODE><<<batch, 64, g.smem, ctx->stream>>>(p);
+    PDEGPU_LAUNCH_CHECK(ctx, "lex_pass_kernel");
+    return PDEGPU_OK;
+}
+
+template <int FAM>
+int lex_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    using F = Fam<FAM>;
+    constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, MODE = F::PDE ? 1 : 0;
+    constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
+    const int nr = sys->nrows, nc = sys->ncols, batch = sys->batch;
+    if (F::PDE && F::EIGHT) iter = 1;                         // pdeSolvers.c:362
+    if (iter <= 0) return PDEGPU_OK;
+    LexGeom g0, g1;
+    if (!lex_geometry(nr, NUNK, NC, g0) || !lex_geometry(nc, NUNK, NC, g1))
+        return pdegpu_set_error(ctx, PDEGPU_ERR_UNSUPPORTED, "reference-order line relaxation: lines of %d / %d elements do not fit the shared memory of an SM", nr, nc);
+    const int pitch0 = (nr + 3) & ~3, pitch1 = (nc + 3) & ~3;
+    const long long F0 = (long long)nc * pitch0, F1 = (long long)nr * pitch1;
+    const size_t bytes_pn = (size_t)NC * F0 * batch * 4, bytes_pt = (size_t)NC * F1 * batch * 4;
+    const size_t bytes_tn = (size_t)NUNK * F0 * batch * 4, bytes_tt = (size_t)NUNK * F1 * batch * 4;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    int rc = pdegpu_scratch_reserve(ctx, up(bytes_pn) + up(bytes_pt) + up(bytes_tn) + up(bytes_tt));
+    if (rc) return rc;
+    char *sp = ctx->scratch;
+    float *PN = (float *)sp; sp += up(bytes_pn);
+    float *PT = (float *)sp; sp += up(bytes_pt);
+    float *TN = (float *)sp; sp += up(bytes_tn);
+    float *TT = (float *)sp;
+    {
+        PrepParams pp;
+        memset(&pp, 0, sizeof(pp));
+        for (int k = 0; k < NN; k++) pp.w[k] = sys->w[k];
+        pp.m = sys->m;
+        for (int q = 0; q < NUNK; q++) { pp.c[q] = sys->c[q]; pp.d[q] = sys->d[q]; pp.x0[q] = sys->x0[q]; pp.x[q] = sys->x[q]; }
+        pp.nrows = nr; pp.ncols = nc; pp.pitch0 = pitch0; pp.pitch1 = pitch1;
+        pp.S0 = 1; pp.ns0 = pitch0 > nr ? pitch0 : nr; pp.S1 = 1; pp.ns1 = pitch1 > nc ? pitch1 : nc;
+        pp.ibs = sys->batch_stride; pp.pn = PN; pp.pt = PT; pp.tn = TN;
+        const size_t smem = (size_t)NC * 32 * 33 * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
+        dim3 grid((pitch0 + 31) / 32, (pitch1 + 31) / 32, batch);
+        PDEGPU_PROF(ctx, "tline_prep_kernel", 0);
+        tline_prep_kernel<FAM><<<grid, 256, smem, ctx->stream>>>(pp);
+        PDEGPU_LAUNCH_CHECK(ctx, "tline_prep_kernel");
+    }
+    LexParams p0, p1;
+    memset(&p0, 0, sizeof(p0));
+    p0.coef = PN; p0.t = TN; p0.pitch = pitch0; p0.q0 = 0; p0.n = nr; p0.nlines = nc; p0.omega = omega;
+    p0.skip_border = (F::PDE && F::EIGHT) ? 1 : 0;
+    p1 = p0;
+    p1.coef = PT; p1.t = TT; p1.pitch = pitch1; p1.q0 = 1; p1.n = nc; p1.nlines = nr;
+    const double pass_bytes = sweep_bytes<FAM>() * (double)nr * nc * batch;
+    for (int it = 0; it < iter; it++) {
+        if ((rc = lex_pass<NUNK, NN, MODE>(ctx, p0, batch, pass_bytes, "lex_pass_kernel<dir0>"))) return rc;
+        {
+            dim3 grid((nr + 31) / 32, (nc + 31) / 32, batch * NUNK);
+            PDEGPU_PROF(ctx, "lex_transpose_kernel", 0);
+            lex_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(TT, TN, nr, nc, pitch0, pitch1, NUNK);
+            PDEGPU_LAUNCH_CHECK(ctx, "lex_transpose_kernel");
+        }
+        if ((rc = lex_pass<NUNK, NN, MODE>(ctx, p1, batch, pass_bytes, "lex_pass_kernel<dir1>"))) return rc;
+        {
+            dim3 grid((nc + 31) / 32, (nr + 31) / 32, batch * NUNK);
+            PDEGPU_PROF(ctx, "lex_transpose_kernel", 0);
+            lex_transpose_kernel<<<grid, 256, 0, ctx->stream>>>(TN, TT, nc, nr, pitch1, pitch0, NUNK);
+            PDEGPU_LAUNCH_CHECK(ctx, "lex_transpose_kernel");
+        }
+    }
+    {
+        FinalParams fp;
+        memset(&fp, 0, sizeof(fp));
+        for (int q = 0; q < NUNK; q++) { fp.x[q] = sys->x[q]; fp.x0[q] = F::LATE ? sys->x0[q] : nullptr; }
+        fp.tn = TN; fp.nunk = NUNK; fp.nrows = nr; fp.ncols = nc; fp.pitch0 = pitch0; fp.xbs = sys->batch_stride;
+        fp.S0 = 1; fp.ns0 = pitch0 > nr ? pitch0 : nr;
+        bool vec = (nr % 4 == 0) && (sys->batch_stride % 4 == 0);
+        for (int q = 0; q < NUNK; q++) vec = vec && (((uintptr_t)sys->x[q] | (uintptr_t)(F::LATE ? sys->x0[q] : nullptr)) & 15) == 0;
+        fp.vec = vec ? 1 : 0;
+        dim3 grid((nr + 1023) / 1024, nc, batch);
+        PDEGPU_PROF(ctx, "tline_final_kernel", 0);
+        tline_final_kernel<<<grid, 256, 0, ctx->stream>>>(fp);
+        PDEGPU_LAUNCH_CHECK(ctx, "tline_final_kernel");
+    }
+    return PDEGPU_OK;
+}
+
 }  // namespace
 
 #ifdef TL_PROBE
@@ -328,12 +601,39 @@ extern "C" int pdegpu_debug_tl_probe(unsigned long long *out32)
 
 int relax_tline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
+    {   // small problems: the whole call in one launch, resident in shared memory
+        int rc = PDEGPU_ERR_UNSUPPORTED;
+        switch (sys->family) {
+        case PDEGPU_FLOW_ELIN4: rc = tline_small_run<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega); break;
+        case PDEGPU_FLOW_LLIN4: rc = tline_small_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega); break;
+        case PDEGPU_DISP_LLIN4: rc = tline_small_run<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega); break;
+        case PDEGPU_PDE4:       rc = tline_small_run<PDEGPU_PDE4>(ctx, sys, iter, omega); break;
+        default: break;
+        }
+        if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
+    }
     switch (sys->family) {
     case PDEGPU_FLOW_ELIN4: return tline_run<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
     case PDEGPU_FLOW_LLIN4: return tline_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
     case PDEGPU_FLOW_LLIN8: return tline_run<PDEGPU_FLOW_LLIN8>(ctx, sys, iter, omega);
     case PDEGPU_DISP_LLIN4: return tline_run<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
     case PDEGPU_PDE4:       return tline_run<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE8:       return tline_run<PDEGPU_PDE8>(ctx, sys, iter, omega);
+    default: return PDEGPU_ERR_UNSUPPORTED;
+    }
+}
+
+// solver 2 in the reference's (lexicographic) line order: pdegpu_set_sweep_order(ctx, PDEGPU_ORDER_REFERENCE)
+int relax_lexline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    if (sys->nrows < 3 || sys->ncols < 3) return PDEGPU_ERR_UNSUPPORTED;
+    switch (sys->family) {
+    case PDEGPU_FLOW_ELIN4: return lex_run<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN4: return lex_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN8: return lex_run<PDEGPU_FLOW_LLIN8>(ctx, sys, iter, omega);
+    case PDEGPU_DISP_LLIN4: return lex_run<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE4:       return lex_run<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE8:       return lex_run<PDEGPU_PDE8>(ctx, sys, iter, omega);
     default: return PDEGPU_ERR_UNSUPPORTED;
     }
 }

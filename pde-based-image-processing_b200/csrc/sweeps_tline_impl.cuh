@@ -142,7 +142,10 @@ tline_pass_kernel(const TLParams p)
             const int n = seg == p.S - 1 ? p.nlast : p.ns;
             const bool cutL = seg > 0, cutR = seg < p.S - 1;
             // values across the cuts, from the start of the pass (global memory; used after the row formulas)
+            const bool odd = flags & 1, eLo = flags & 2, eHi = flags & 4, owned = flags & 8, relaxed = !(flags & 16);
             float hL0 = 0.f, hL1 = 0.f, hR0 = 0.f, hR1 = 0.f;
+            // 8-neighbour stencils: the diagonal neighbours across a cut, [lo/hi line][left/right cut][unknown]
+            float hD[2][2][NUNK] = {};
             if (lane == 0 && (cutL || cutR)) {
                 const long long ls = (long long)NUNK * P;
                 const float *tl = p.tin + ((long long)(pi - 1) * nlines + d0.w) * ls + (p.ns - 1);
@@ -150,8 +153,16 @@ tline_pass_kernel(const TLParams p)
                 const int u0 = (NUNK == 2 ? p.q0 : 0) * P, u1 = (NUNK == 2 ? (p.q0 ^ 1) : 0) * P;
                 if (cutL) { hL0 = tl[u0]; if (NUNK == 2) hL1 = tl[u1]; }
                 if (cutR) { hR0 = tr[u0]; if (NUNK == 2) hR1 = tr[u1]; }
+                if (NN == 8) {
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        if (!(h == 0 ? eLo : eHi)) continue;
+                        const long long dl = (h == 0 ? -1 : 1) * ls;
+                        if (cutL) { hD[h][0][0] = tl[dl + u0]; if (NUNK == 2) hD[h][0][NUNK - 1] = tl[dl + u1]; }
+                        if (cutR) { hD[h][1][0] = tr[dl + u0]; if (NUNK == 2) hD[h][1][NUNK - 1] = tr[dl + u1]; }
+                    }
+                }
             }
-            const bool odd = flags & 1, eLo = flags & 2, eHi = flags & 4, owned = flags & 8, relaxed = !(flags & 16);
             const int gh = l + BL + 1;
             // ring slots g % R, (g -+ 1) % R and their use counts g / R, (g -+ 1) / R (g = l + BL)
             const int rs = d1.z, rlo = rs == 0 ? R - 1 : rs - 1, rhi = rs == R - 1 ? 0 : rs + 1;
@@ -184,11 +195,12 @@ tline_pass_kernel(const TLParams p)
                 // is padded so that lanes past the end of a short line read (and discard) whatever follows.
                 {
                     float *sw_ = const_cast<float *>(sl);
-                    if (lane == 0) {                          // (at a cut the neighbour exists: see below)
+                    if (NN == 4 && lane == 0) {               // (at a cut the neighbour exists: see below)
                         if (!cutL) sw_[rWP * P] = 0.f;
                         if (!cutR) sw_[rWN * P + n - 1] = 0.f;
-                        if (NN == 8) { sw_[(rDG + 0) * P] = 0.f; sw_[(rDG + 2) * P] = 0.f; sw_[(rDG + 1) * P + n - 1] = 0.f; sw_[(rDG + 3) * P + n - 1] = 0.f; }
                     }
+                    // (8-neighbour families mask the ends in the row formulas: the NaN-TRACE diagonal of pdeSolvers.c:1179
+                    // wants the weights as they are, and the diagonal neighbours across a cut are added after the loop)
                     if (!eLo || !eHi) {
                         for (int e = lane; e < n; e += 32) {
                             if (!eLo) { sw_[rWL * P + e] = 0.f; if (NN == 8) { sw_[(rDG + 0) * P + e] = 0.f; sw_[(rDG + 1) * P + e] = 0.f; } }
@@ -205,26 +217,39 @@ tline_pass_kernel(const TLParams p)
                 for (int k = 0; k < M; k++) {
                     const int e = o + k;
                     const bool ok = e < n;
-                    const float wp = sl[rWP * P + e], wn = sl[rWN * P + e], wl = sl[rWL * P + e], wh = sl[rWH * P + e];
+                    float wp = sl[rWP * P + e], wn = sl[rWN * P + e];
+                    const float wl = sl[rWL * P + e], wh = sl[rWH * P + e];
+                    const float wp_raw = wp, wn_raw = wn;
+                    if (NN == 8) {                            // ends of the line (not of a segment): no neighbour
+                        if (e == 0 && !cutL) wp = 0.f;
+                        if (e == n - 1 && !cutR) wn = 0.f;
+                    }
                     float sw = (wl + wh) + (wp + wn);
                     float cr0 = wl * lo[t0 + e] + wh * hi[t0 + e];
                     float cr1 = 0.f;
                     if (NUNK == 2) cr1 = wl * lo[t1 + e] + wh * hi[t1 + e];
+                    float quirk = 0.f;
                     if (NN == 8) {
-                        // diagonal neighbours: elements e-1 / e+1 of the two lines. At the ends of the line their weights
-                        // are zero (patched above) and the index is kept inside the line (0 * NaN = NaN)
-                        const int em = e > 0 ? e - 1 : 0, ep = min(e + 1, n - 1);
-                        const float wlp = sl[(rDG + 0) * P + e], wln = sl[(rDG + 1) * P + e];
-                        const float whp = sl[(rDG + 2) * P + e], whn = sl[(rDG + 3) * P + e];
+                        // diagonal neighbours: elements e-1 / e+1 of the two lines; none at the first / last element of the
+                        // SEGMENT here (those across a cut are added after the loop)
+                        const bool eP = e > 0, eN = e < n - 1;
+                        const int em = eP ? e - 1 : 0, ep = eN ? e + 1 : e;
+                        const float rlp = sl[(rDG + 0) * P + e], rln = sl[(rDG + 1) * P + e];
+                        const float rhp = sl[(rDG + 2) * P + e], rhn = sl[(rDG + 3) * P + e];
+                        const float wlp = eP ? rlp : 0.f, wln = eN ? rln : 0.f, whp = eP ? rhp : 0.f, whn = eN ? rhn : 0.f;
                         sw += (wlp + wln) + (whp + whn);
                         cr0 += (wlp * lo[t0 + em] + wln * lo[t0 + ep]) + (whp * hi[t0 + em] + whn * hi[t0 + ep]);
                         if (NUNK == 2) cr1 += (wlp * lo[t1 + em] + wln * lo[t1 + ep]) + (whp * hi[t1 + em] + whn * hi[t1 + ep]);
+                        // pdeSolvers.c:1179,1209,1238 / :1314,1344,1373: where TRACE is NaN the diagonal is the four
+                        // axial weights + wNW twice + wSW + wSE, whatever the position (wNE never). In line roles: column
+                        // pass NW SW SE = LP LN HN, row pass = LP HP HN
+                        if (MODE == 1) quirk = ((wp_raw + wn_raw) + (wl + wh)) + ((rlp + rlp) + ((p.q0 ? rhp : rln) + rhn));
                     }
                     const float C = sl[rC * P + e], Dd = sl[rD * P + e];
                     float bb, dd;
                     if (MODE == 1) {
                         const bool has = !is_nan(Dd);
-                        bb = has ? Dd : sw;
+                        bb = has ? Dd : (NN == 8 ? quirk : sw);
                         dd = has ? cr0 + C : cr0;
                     } else {
                         const bool has = !is_nan(C);
@@ -244,8 +269,6 @@ tline_pass_kernel(const TLParams p)
                         ms[k] = has ? sl[rMM * P + e] : 0.f;                       // coupling to the NEW first unknown, added after its solve
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);     // rows are in registers: the slab can be refilled
                 if (cutL || cutR) {
                     // ends of a segment that are not ends of the line: the weight stays in the diagonal, the neighbour's
                     // value (start of the pass) goes to the right-hand side, the row is cut off from the recurrence
@@ -253,17 +276,36 @@ tline_pass_kernel(const TLParams p)
                     if (cutL && lane == 0) {
                         d[0] -= a[0] * hL0; a[0] = 0.f;
                         if (NUNK == 2) { ds[0] -= as[0] * hL1; as[0] = 0.f; }
+                        if (NN == 8) {                        // its diagonal neighbours on the lines j-1 / j+1
+                            const float rlp = sl[(rDG + 0) * P], rhp = sl[(rDG + 2) * P];
+                            d[0] += rlp * hD[0][0][0] + rhp * hD[1][0][0];
+                            if (NUNK == 2) ds[0] += rlp * hD[0][0][NUNK - 1] + rhp * hD[1][0][NUNK - 1];
+                            if (MODE == 0) { b[0] += rlp + rhp; if (NUNK == 2) bs[0] += rlp + rhp; }
+                        }
                     }
                     if (cutR) {
+                        float dl0 = 0.f, dl1 = 0.f, dh0 = 0.f, dh1 = 0.f, rln = 0.f, rhn = 0.f;
+                        if (NN == 8) {
+                            dl0 = __shfl_sync(FULLMASK, hD[0][1][0], 0); dh0 = __shfl_sync(FULLMASK, hD[1][1][0], 0);
+                            if (NUNK == 2) { dl1 = __shfl_sync(FULLMASK, hD[0][1][NUNK - 1], 0); dh1 = __shfl_sync(FULLMASK, hD[1][1][NUNK - 1], 0); }
+                            rln = sl[(rDG + 1) * P + n - 1]; rhn = sl[(rDG + 3) * P + n - 1];
+                        }
 #pragma unroll
                         for (int k = 0; k < M; k++)
                             if (o + k == n - 1) {
                                 d[k] -= c[k] * hR0;
                                 if (NUNK == 2) ds[k] -= c[k] * hR1;
                                 c[k] = 0.f;
+                                if (NN == 8) {
+                                    d[k] += rln * dl0 + rhn * dh0;
+                                    if (NUNK == 2) ds[k] += rln * dl1 + rhn * dh1;
+                                    if (MODE == 0) { b[k] += rln + rhn; if (NUNK == 2) bs[k] += rln + rhn; }
+                                }
                             }
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);     // rows are in registers: the slab can be refilled
                 TLP(3);
 #pragma unroll 1
                 for (int q = 0; q < NUNK; q++) {

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get("PDEGPU_LIB") or os.path.join(os.path.dirname(_HERE), "libpdegpu.so")
 
 FLOW_ELIN4, FLOW_LLIN4, FLOW_LLIN8, DISP_LLIN4, PDE4, PDE8 = range(6)
+ORDER_FAST, ORDER_REFERENCE = 0, 1
 W_W, W_N, W_E, W_S, W_NW, W_NE, W_SE, W_SW = range(8)
 
 OK = 0
@@ -121,6 +122,10 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_launch_count.argtypes = [c_void_p]
         L.pdegpu_set_kernel_path.restype = c_int
         L.pdegpu_set_kernel_path.argtypes = [c_void_p, c_int]
+        L.pdegpu_set_sweep_order.restype = c_int
+        L.pdegpu_set_sweep_order.argtypes = [c_void_p, c_int]
+        L.pdegpu_get_sweep_order.restype = c_int
+        L.pdegpu_get_sweep_order.argtypes = [c_void_p]
         L.pdegpu_dev_relax.restype = c_int
         L.pdegpu_dev_relax.argtypes = [c_void_p, POINTER(System), c_int, c_float, c_int]
         L.pdegpu_dev_residual.restype = c_int
@@ -238,6 +243,10 @@ class Context:
 
     def set_kernel_path(self, path: int):
         self._chk(dll().pdegpu_set_kernel_path(self.h, path))
+
+    def set_sweep_order(self, order: int):
+        """ORDER_FAST (zebra) or ORDER_REFERENCE (the reference's lexicographic line order), solver 2 only"""
+        self._chk(dll().pdegpu_set_sweep_order(self.h, order))
 
     def profile(self, on: bool):
         self._chk(dll().pdegpu_profile_enable(self.h, 1 if on else 0))

@@ -85,3 +85,13 @@ def test_gateways_reject_non_single_and_bad_counts(built):
                   ("SndDerivatives5", 2), ("DdiffWeights", 2)):
         with pytest.raises(mex.MexError):
             mex.call(fn, [synth.f32(np.zeros((6, 6)))] * (n + 1), 5)
+
+
+def test_batch_cli_builds_and_rejects_bad_usage(built):
+    """pdegpu_flow_batch: plain C on the C ABI; without arguments it prints its usage and exits 2
+    (no GPU is touched before the arguments are valid)."""
+    import subprocess
+    exe = built.build_cli()
+    assert exe and os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: pdegpu_flow_batch" in r.stderr

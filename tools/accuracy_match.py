@@ -28,7 +28,7 @@ ctx = lib.Context(0)
 sl = (slice(8, -8), slice(8, -8))
 out = {"driver": which, "nrows": nr, "ncols": nc, "pairs": []}
 for seed in (300, 311):
-    I0, I1, u, v = synth.image_pair(seed, nr, nc, nframes=1, scale=255.0 if which == "fmg" else 1.0, max_flow=0.8)
+    I0, I1, u, v = synth.image_pair(seed, nr, nc, nframes=1, scale=255.0, max_flow=0.8)     # both drivers take 0..255 frames (HS divides by 255 itself, FlowEminHS_elin_2D_v10.m:67)
     I0, I1 = I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1)
 
     def aee(U, V):
