@@ -78,8 +78,9 @@ def parse():
     ap.add_argument("--band-iters", type=int, default=8, help="red-black sweeps per step")
     ap.add_argument("--band-T", type=int, default=1, help="sweeps per halo exchange (halo = 2T columns)")
     ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
+    ap.add_argument("--flow-ref-batch", type=int, default=64, help="640x480 pairs per GPU for the flows/s leg in the reference's line order (0 = skip)")
     ap.add_argument("--sweep-legs", type=int, default=1, help="relaxation sweep alone at 1080p / 4096x2160 / point solver (0 = skip)")
-    ap.add_argument("--fmg-pairs", type=int, default=2, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
+    ap.add_argument("--fmg-pairs", type=int, default=8, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -248,10 +249,13 @@ def timed_median(fn, reps, stream, barrier):
     return float(np.median(ts))
 
 
-def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
+def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=5, order=None, cpu=True):
+    """order None: the library's default for this driver (AUTO -> zebra for the late-linearisation family);
+    lib.ORDER_REFERENCE: the reference's line order (iterates, hence the flow, equal to the reference's)"""
     import torch
     from pdegpu import lib, synth
     C = 3
+    ctx.set_sweep_order(lib.ORDER_AUTO if order is None else order)
     L = lib.dll()
     p = lib.FlowLlinParams()
     L.pdegpu_flow_llin_default_params(ctypes.byref(p))
@@ -300,12 +304,14 @@ def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
     Ug = U[0].cpu().numpy().reshape(NROWS, NCOLS, order="F"); Vg = V[0].cpu().numpy().reshape(NROWS, NCOLS, order="F")
     sl = (slice(8, -8), slice(8, -8))
     aee = float(np.mean(np.sqrt((Ug[sl] - u[sl]) ** 2 + (Vg[sl] - v[sl]) ** 2)))
+    ctx.set_sweep_order(lib.ORDER_FAST)
     out = {"metric": "640x480 flows/s (FlowEminND_llin_2D_v10 defaults: 13 levels, firstLoop=4, secondLoop=4, ALR iter=4, 'grad'+'gradmag', RGB)",
+           "order": "reference (lexicographic lines: the reference's iterates)" if order == lib.ORDER_REFERENCE else "fast (zebra lines; library default for this driver)",
            "value": world * FB / (ms / 1e3), "unit": "flows/s", "batch_per_gpu": FB, "ms_per_batch": ms,
            "gpu_launches_per_batch": int(launches), "aee_vs_ground_truth_px": aee,
            "e2e": {"value": world * FB / e2e_s, "unit": "flows/s", "h2d_bytes_per_step": int(2 * h0.nbytes),
                    "d2h_bytes_per_step": int(2 * FB * NROWS * NCOLS * 4), "api": "pdegpu_flow_llin_2d (host pointers, pinned)"}}
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and cpu:
         from oracle import oracle as orc, pipelines
         be = orc.RefBackend() if orc.have_ref() else orc.OracleBackend()
         t0 = time.perf_counter()
@@ -372,6 +378,12 @@ def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
         Ug = U[0].cpu().numpy().reshape(NR, NC, order="F"); Vg = V[0].cpu().numpy().reshape(NR, NC, order="F")
         return ms, (ctx.launches - l0) // reps, aee_of(Ug, Vg)
 
+    # the library's default order for this driver is the reference's (include/pdegpu.h: PDEGPU_ORDER_AUTO): same iterates,
+    # same flow as the reference at the driver's iteration counts. The zebra order (fast_order) is quoted next to it
+    # with ITS accuracy: the two numbers are not the same answer.
+    ctx.set_sweep_order(lib.ORDER_FAST)
+    ms_f, launches_f, aee_f = timed(p)
+    ctx.set_sweep_order(lib.ORDER_AUTO)
     ms, launches, aee = timed(p)
     for _ in range(3):
         host_run()
@@ -381,9 +393,13 @@ def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
         host_run()
     barrier()
     e2e_s = maxr(time.perf_counter() - t0) / reps
+    ctx.set_sweep_order(lib.ORDER_FAST)
     out = {"metric": "1920x1080 flows/s (FlowEminNDFASFMG_elin_2D_v10 defaults: FMG, FAS V-cycle per level, firstLoop=4, ALR iter=4, 1 channel)",
+           "order": "reference (lexicographic lines: the reference's iterates; library default for this driver), pairs side by side on lanes",
            "value": world * FB / (ms / 1e3), "unit": "flows/s", "pairs_per_gpu": FB, "ms_per_pair": ms / FB,
            "gpu_launches_per_pair": int(launches // FB), "aee_vs_ground_truth_px": aee,
+           "fast_order": {"order": "fast (zebra lines)", "value": world * FB / (ms_f / 1e3), "unit": "flows/s", "ms_per_pair": ms_f / FB,
+                          "gpu_launches_per_pair": int(launches_f // FB), "aee_vs_ground_truth_px": aee_f},
            "e2e": {"value": world * FB / e2e_s, "unit": "flows/s", "h2d_bytes_per_step": int(2 * h0.nbytes),
                    "d2h_bytes_per_step": int(2 * FB * NR * NC * 4), "api": "pdegpu_flow_fmg_2d (host pointers, pinned)"}}
     if rank == 0 and world == 1:
@@ -461,6 +477,10 @@ SWEEP_LEGS = [
     ("sweep_4096x2160", "Disp_sor_llin_sym4_2d = two Disp llin4 systems (finest level of configs[3], DispEminND_llin_sym_2D.m:227-246)", "disp", 2160, 4096, 4, 2, 4, 1.9, 36.0),
     ("sweep_tv_4096x2160", "PDEsolver4 (TVdenoise4.m:85-90 at the configs[3] image size)", "pde4", 2160, 4096, 4, 2, 4, 1.75, 32.0),
     ("point_480x640", "Oflow_sor_llin4_2d solver 1 (red-black point SOR)", "llin4", 480, 640, 64, 1, 4, 1.9, 60.0),
+    # the reference's own line order (one CTA per problem, three problems per SM): latency-bound by construction, quoted
+    # for what it costs to get the reference's iterates
+    ("reference_order_480x640", "Oflow_sor_llin4_2d solver 2 in the reference's lexicographic line order (PDEGPU_ORDER_REFERENCE)", "llin4", 480, 640, 444, 2, 4, 1.9, 60.0),
+    ("reference_order_1080p", "Oflow_sor_elin4_2d solver 2 in the reference's line order, whole lines of 1080 / 1920 elements", "elin4", 1080, 1920, 148, 2, 4, 1.9, 52.0),
 ]
 
 
@@ -470,6 +490,8 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
     peak, peak_src = measured_peaks()
     out = {}
     for name, what, fam, nr, nc, batch, solver, iters, omega, b1 in SWEEP_LEGS:
+        ref_order = name.startswith("reference_order")
+        ctx.set_sweep_order(lib.ORDER_REFERENCE if ref_order else lib.ORDER_FAST)
         f = device_system(torch, dev, fam, nr, nc, batch, 777 + rank)
         sysd, unk = device_sysd(lib, fam, f, nr, nc, batch)
         x0 = [f[k].clone() for k in unk]
@@ -480,7 +502,7 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
             if dist is not None:
                 dist.barrier()
 
-        for _ in range(3):
+        for _ in range(1 if ref_order else 3):
             ctx.relax(sysd, iters, omega, solver)
         for k, v in zip(unk, x0):
             f[k].copy_(v)
@@ -488,11 +510,12 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
         ctx.profile(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
-        for _ in range(steps):
+        nsteps = 2 if ref_order else steps
+        for _ in range(nsteps):
             ctx.relax(sysd, iters, omega, solver)
         ev1.record(stream)
         barrier()
-        ms = ev0.elapsed_time(ev1)
+        ms = ev0.elapsed_time(ev1) * steps / nsteps
         prof = ctx.profile_report()
         ctx.profile(False)
         if dist is not None:
@@ -502,7 +525,7 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
         assert torch.isfinite(f[unk[0]]).all()
         top = max((p for p in prof if p["bytes_total"] > 0 and "prep" not in p["kernel"] and "final" not in p["kernel"] and "transpose" not in p["kernel"]),
                   key=lambda p: p["ms_total"], default=None)
-        leg = {"what": what, "family": fam, "nrows": nr, "ncols": nc, "problems_per_gpu": batch, "solver": solver, "iter": iters, "omega": omega,
+        leg = {"what": what, "order": "reference" if ref_order else "fast", "family": fam, "nrows": nr, "ncols": nc, "problems_per_gpu": batch, "solver": solver, "iter": iters, "omega": omega,
                "value": world * batch * nr * nc * iters * steps / 1e6 / (ms / 1e3), "unit": UNIT, "ms_per_call": ms / steps,
                "l2": f"{(b1 / 4) * batch * nr * nc * 4 / 1e6:.0f} MB of fields per sweep vs 126 MB L2",
                "algorithmic_bytes_per_px_sweep": b1,
@@ -514,6 +537,7 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
                                "algorithmic_bytes_per_launch": top["bytes_total"] / top["launches"], "traffic": None}
         leg["kernels"] = prof
         out[name] = leg
+        ctx.set_sweep_order(lib.ORDER_FAST)
         del f, x0
         torch.cuda.empty_cache()
     return out
@@ -629,6 +653,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     ctx = lib.Context(local)
     ctx.set_kernel_path(1 if args.kernels == "stream" else 0)
+    # headline metric and sweep legs: the zebra order (PDEGPU_ORDER_FAST); the legs that run the reference's line order
+    # say so ("order": "reference") and switch it themselves
+    ctx.set_sweep_order(lib.ORDER_FAST)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     B = args.batch
@@ -723,6 +750,9 @@ def run_ours(args):
     assert os.environ.get("PDEGPU_DBG") or np.isfinite(out0.numpy()).all()
 
     flows = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_batch) if args.flow_batch > 0 else None
+    if flows is not None and args.flow_ref_batch > 0:
+        from pdegpu import lib as _lib
+        flows["reference_order"] = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_ref_batch, reps=3, order=_lib.ORDER_REFERENCE, cpu=False)
     fmg = fmg_leg(ctx, dev, stream, dist, world, rank, args.fmg_pairs) if args.fmg_pairs > 0 else None
     sweeps = sweep_legs(ctx, dev, stream, dist, world, rank) if args.sweep_legs else None
 

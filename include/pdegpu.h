@@ -78,20 +78,28 @@ int         pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen);
  * 1 = streaming register/shared-memory kernels (default). */
 int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);
 /* Order in which solver 2 (alternating line relaxation) visits the lines of a direction.
- *   PDEGPU_ORDER_FAST (default): zebra -- even lines, then odd lines; every line of a colour in parallel. Same fixed
- *     point as the reference, the HBM-bound kernel of the throughput numbers; its iterate after a FEW sweeps differs
- *     from the reference's (information travels two lines per sweep instead of across the image).
+ *   PDEGPU_ORDER_FAST: zebra -- even lines, then odd lines; every line of a colour in parallel. Same fixed point as the
+ *     reference, the HBM-bound kernel of the throughput numbers; its iterate after a FEW sweeps differs from the
+ *     reference's (information travels two lines per sweep instead of across the image).
  *   PDEGPU_ORDER_REFERENCE: the reference's own order -- line j sees the new line j-1 and the old line j+1
  *     (GS_ALR_SOR_*: opticalflowSolvers.c:196,690,1677; disparitySolvers.c:154; pdeSolvers.c:277,344). Iterates agree
- *     with the reference sweep by sweep (fp32 rounding apart), so the unchanged .m drivers give the reference's flow at
- *     the reference's iteration counts. Serial from line to line: the parallelism is the batch (one CTA per problem)
- *     and the lanes inside a line. Also selected by the environment variable PDEGPU_ORDER=reference (for callers that
- *     never see the context: the MEX gateways).
- * Solver 1 (point relaxation) is not affected. Applies to pdegpu_dev_relax and everything built on it. */
+ *     with the reference sweep by sweep (1e-5 of the field's range, tests/test_gpu_reference_order.py), so the unchanged
+ *     .m drivers give the reference's flow at the reference's iteration counts. Serial from line to line: the
+ *     parallelism is the batch (one CTA per problem, several per SM) and the lanes inside a line.
+ *   PDEGPU_ORDER_AUTO (default): REFERENCE for the early-linearisation flow family (PDEGPU_FLOW_ELIN4, i.e. the
+ *     Horn-Schunck and FMG drivers, which solve each level ONCE and never re-warp: the iterate after `iter` sweeps is
+ *     their result, and at their default iter = 20 / 4 the zebra iterate is a measurably different flow -- Yosemite
+ *     FMG: 0.69 px against the reference's 0.21 px average end-point error); FAST for every other family (their
+ *     drivers re-warp and re-linearise, both orders recover the ground truth equally well at the default settings).
+ * The environment variable PDEGPU_ORDER = reference | fast | auto sets the initial order of a context; the MEX gateways
+ * (which own their context) follow it at every call. Solver 1 (point relaxation) is not affected. Applies to
+ * pdegpu_dev_relax and everything built on it (host-pointer entry points, driver pipelines). */
 #define PDEGPU_ORDER_FAST      0
 #define PDEGPU_ORDER_REFERENCE 1
+#define PDEGPU_ORDER_AUTO      2
 int         pdegpu_set_sweep_order(pdegpu_ctx *ctx, int order);
 int         pdegpu_get_sweep_order(const pdegpu_ctx *ctx);
+int         pdegpu_order_from_env(void);                    /* what PDEGPU_ORDER says right now (AUTO if unset) */
 
 /* Device / pinned memory owned by the library (for the pdegpu_dev_* entry points). */
 int         pdegpu_malloc(pdegpu_ctx *ctx, void **dptr, size_t bytes);

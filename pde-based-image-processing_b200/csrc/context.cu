@@ -55,8 +55,7 @@ extern "C" int pdegpu_init(int device, pdegpu_ctx **out)
     ctx->kernel_path = 1;
     const char *env = getenv("PDEGPU_KERNELS");
     if (env && strcmp(env, "simple") == 0) ctx->kernel_path = 0;
-    env = getenv("PDEGPU_ORDER");
-    if (env && strcmp(env, "reference") == 0) ctx->sweep_order = PDEGPU_ORDER_REFERENCE;
+    ctx->sweep_order = pdegpu_order_from_env();
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { free(ctx); return pdegpu_check_cuda(nullptr, e, "cudaStreamCreate"); }
     *out = ctx;
@@ -157,11 +156,68 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
     }
     pdegpu_graphs_drop(ctx);
     free(ctx->graphs);
+    for (int k = 0; k < ctx->nlanes; k++) pdegpu_free(ctx->lanes[k]);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->work) cudaFree(ctx->work);
     cudaStreamDestroy(ctx->stream);
     free(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// lanes (pdegpu_internal.cuh)
+// ---------------------------------------------------------------------------------------------
+int pdegpu_lane_count(pdegpu_ctx *ctx, int batch)
+{
+    static const int max_lanes = getenv("PDEGPU_LANES") ? atoi(getenv("PDEGPU_LANES")) : 16;
+    if (ctx->prof_on || ctx->parent || batch < 2 || max_lanes < 2) return 1;
+    const int cap = (int)(sizeof(ctx->lanes) / sizeof(ctx->lanes[0]));
+    int n = batch < max_lanes ? batch : max_lanes;
+    return n < cap ? n : cap;
+}
+
+int pdegpu_lanes_prepare(pdegpu_ctx *ctx, int n, size_t work_bytes, const char *who)
+{
+    if (!ctx->ev_fork) {
+        PDEGPU_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    }
+    while (ctx->nlanes < n) {
+        pdegpu_ctx *c = (pdegpu_ctx *)calloc(1, sizeof(pdegpu_ctx));
+        if (!c) return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "%s: out of host memory", who);
+        c->device = ctx->device; c->sm_count = ctx->sm_count; c->parent = ctx;
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) { free(c); return pdegpu_check_cuda(ctx, e, "lane stream"); }
+        ctx->lanes[ctx->nlanes++] = c;
+    }
+    for (int k = 0; k < n; k++) {
+        pdegpu_ctx *c = ctx->lanes[k];
+        c->kernel_path = ctx->kernel_path; c->sweep_order = ctx->sweep_order; c->capturing = 1;   // (a lane never builds graphs of its own)
+        const int rc = pdegpu_work_reserve(c, work_bytes, who);
+        if (rc) { memcpy(ctx->err, c->err, sizeof ctx->err); return rc; }
+    }
+    return PDEGPU_OK;
+}
+
+int pdegpu_lanes_fork(pdegpu_ctx *ctx, int n)
+{
+    PDEGPU_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int k = 0; k < n; k++) PDEGPU_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->lanes[k]->stream, ctx->ev_fork, 0));
+    return PDEGPU_OK;
+}
+
+int pdegpu_lanes_join(pdegpu_ctx *ctx, int n)
+{
+    for (int k = 0; k < n; k++) {
+        pdegpu_ctx *c = ctx->lanes[k];
+        PDEGPU_CUDA_OK(ctx, cudaEventRecord(c->ev_join, c->stream));
+        PDEGPU_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, c->ev_join, 0));
+        ctx->launches += c->launches;
+        c->launches = 0;
+    }
+    return PDEGPU_OK;
 }
 
 extern "C" int pdegpu_sync(pdegpu_ctx *ctx)
@@ -242,9 +298,17 @@ extern "C" int pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path)
     return PDEGPU_OK;
 }
 
+extern "C" int pdegpu_order_from_env(void)
+{
+    const char *env = getenv("PDEGPU_ORDER");
+    if (env && strcmp(env, "reference") == 0) return PDEGPU_ORDER_REFERENCE;
+    if (env && strcmp(env, "fast") == 0) return PDEGPU_ORDER_FAST;
+    return PDEGPU_ORDER_AUTO;
+}
+
 extern "C" int pdegpu_set_sweep_order(pdegpu_ctx *ctx, int order)
 {
-    if (!ctx || (order != PDEGPU_ORDER_FAST && order != PDEGPU_ORDER_REFERENCE)) return PDEGPU_ERR_ARG;
+    if (!ctx || order < PDEGPU_ORDER_FAST || order > PDEGPU_ORDER_AUTO) return PDEGPU_ERR_ARG;
     if (ctx->sweep_order != order) ctx->graph_epoch++;     // captured graphs hold the other order's kernels
     ctx->sweep_order = order;
     return PDEGPU_OK;
@@ -289,6 +353,7 @@ int pdegpu_scratch_reserve(pdegpu_ctx *ctx, size_t bytes)
     PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->scratch) { cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
     ctx->graph_epoch++;
+    if (ctx->parent) ctx->parent->graph_epoch++;
     size_t want = bytes + (bytes >> 3) + (1u << 20);
     cudaError_t e = cudaMalloc((void **)&ctx->scratch, want);
     if (e != cudaSuccess) {
@@ -309,6 +374,7 @@ int pdegpu_work_reserve(pdegpu_ctx *ctx, size_t bytes, const char *who)
     if (ctx->work) cudaFree(ctx->work);
     ctx->work = nullptr; ctx->work_bytes = 0;
     ctx->graph_epoch++;
+    if (ctx->parent) ctx->parent->graph_epoch++;
     if (cudaMalloc((void **)&ctx->work, bytes) != cudaSuccess) {
         cudaGetLastError();
         return pdegpu_set_error(ctx, PDEGPU_ERR_NOMEM, "%s: cannot allocate %zu bytes of workspace", who, bytes);

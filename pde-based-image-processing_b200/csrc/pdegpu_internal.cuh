@@ -39,8 +39,24 @@ struct pdegpu_ctx {
     unsigned long long graph_tick;
     int           capturing;
     struct pdegpu_graph_entry *graphs;
+    // LANES: child contexts (own stream, scratch, workspace) on which the pairs of a batch run side by side where a
+    // driver pipeline is written for one pair (FMG, Horn-Schunck, symmetric stereo): see pdegpu_lanes_* below
+    struct pdegpu_ctx *parent;
+    struct pdegpu_ctx *lanes[32];
+    int           nlanes;
+    cudaEvent_t   ev_fork, ev_join;
     char          err[512];
 };
+
+// Pairs of a batch on parallel streams. pdegpu_lane_count: how many lanes a batch of `batch` pairs gets (1 = run on
+// the context itself: while profiling, or with PDEGPU_LANES=1). prepare: the lanes exist, carry the context's current
+// settings and own at least `work_bytes` of workspace each. fork / join: the lanes' streams wait for everything
+// enqueued on the context's stream / the context's stream waits for the lanes (both legal inside a stream capture:
+// the captured graph then has one branch per lane).
+int pdegpu_lane_count(pdegpu_ctx *ctx, int batch);
+int pdegpu_lanes_prepare(pdegpu_ctx *ctx, int n, size_t work_bytes, const char *who);
+int pdegpu_lanes_fork(pdegpu_ctx *ctx, int n);
+int pdegpu_lanes_join(pdegpu_ctx *ctx, int n);
 
 // Runs `body` (a sequence of launches on ctx->stream with no host synchronisation) and, from the second call with the
 // same `key` on, replays it as a CUDA graph: the pipelines issue thousands of small dependent launches per call (4400

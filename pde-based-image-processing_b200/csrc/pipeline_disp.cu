@@ -172,20 +172,26 @@ extern "C" int pdegpu_dev_disp_sym_2d(pdegpu_ctx *ctx, float *U, const float *Il
     Bump2 dry = {nullptr, 0, true};
     int rc = disp_run(ctx, dry, U, Il, Ir, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if ((rc = pdegpu_work_reserve(ctx, dry.used, "pdegpu_dev_disp_sym_2d"))) return rc;
-    struct Args { pdegpu_ctx *ctx; float *U; const float *Il, *Ir; int nrows, ncols, channels, batch; pdegpu_disp_sym_params P; char *work; int id; };
+    // pairs of a batch run side by side on the context's lanes (one workspace each); a single pair on the context itself
+    const int K = pdegpu_lane_count(ctx, batch);
+    if ((rc = K > 1 ? pdegpu_lanes_prepare(ctx, K, dry.used, "pdegpu_dev_disp_sym_2d") : pdegpu_work_reserve(ctx, dry.used, "pdegpu_dev_disp_sym_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U; const float *Il, *Ir; int nrows, ncols, channels, batch; pdegpu_disp_sym_params P; char *work; int id, K; };
     Args a;
     memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
     a.ctx = ctx; a.U = U; a.Il = Il; a.Ir = Ir; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
-    a.P = *params; a.work = ctx->work; a.id = 4;
+    a.P = *params; a.work = K > 1 ? ctx->lanes[0]->work : ctx->work; a.id = 4; a.K = K;
     pdegpu_graph_body body = {[](void *p) -> int {
         Args &a = *static_cast<Args *>(p);
         const size_t np = (size_t)a.nrows * a.ncols;
+        int rc;
+        if (a.K > 1 && (rc = pdegpu_lanes_fork(a.ctx, a.K))) return rc;
         for (int bi = 0; bi < a.batch; bi++) {
-            Bump2 w = {a.work, 0, false};
-            const int rc = disp_run(a.ctx, w, a.U + 2 * bi * np, a.Il + bi * np * a.channels, a.Ir + bi * np * a.channels, a.nrows, a.ncols, a.channels, a.P);
-            if (rc) return rc;
+            pdegpu_ctx *c = a.K > 1 ? a.ctx->lanes[bi % a.K] : a.ctx;
+            Bump2 w = {c->work, 0, false};
+            rc = disp_run(c, w, a.U + 2 * bi * np, a.Il + bi * np * a.channels, a.Ir + bi * np * a.channels, a.nrows, a.ncols, a.channels, a.P);
+            if (rc) { if (c != a.ctx) memcpy(a.ctx->err, c->err, sizeof c->err); return rc; }
         }
+        if (a.K > 1 && (rc = pdegpu_lanes_join(a.ctx, a.K))) return rc;
         return PDEGPU_OK;
     }, &a};
     return pdegpu_graph_run(ctx, &a, sizeof a, body);

@@ -297,21 +297,26 @@ extern "C" int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const
     Stack dry = {nullptr, 0, 0, true};
     int rc = fmg_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if ((rc = pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_fmg_2d"))) return rc;
-    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_fmg_params P; char *work; int id; };
+    // pairs of a batch run side by side on the context's lanes (one workspace each); a single pair on the context itself
+    const int K = pdegpu_lane_count(ctx, batch);
+    if ((rc = K > 1 ? pdegpu_lanes_prepare(ctx, K, dry.peak, "pdegpu_dev_flow_fmg_2d") : pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_fmg_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_fmg_params P; char *work; int id, K; };
     Args a;
     memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
     a.ctx = ctx; a.U = U; a.V = V; a.I0 = I0; a.I1 = I1; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
-    a.P = *params; a.work = ctx->work; a.id = 2;
+    a.P = *params; a.work = K > 1 ? ctx->lanes[0]->work : ctx->work; a.id = 2; a.K = K;
     pdegpu_graph_body body = {[](void *p) -> int {
         Args &a = *static_cast<Args *>(p);
         const size_t np = (size_t)a.nrows * a.ncols;
+        if (a.K > 1) RC(pdegpu_lanes_fork(a.ctx, a.K));
         for (int bi = 0; bi < a.batch; bi++) {
-            Stack w = {a.work, 0, 0, false};
-            const int rc = fmg_run(a.ctx, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
+            pdegpu_ctx *c = a.K > 1 ? a.ctx->lanes[bi % a.K] : a.ctx;
+            Stack w = {c->work, 0, 0, false};
+            const int rc = fmg_run(c, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
                                    a.nrows, a.ncols, a.channels, a.P);
-            if (rc) return rc;
+            if (rc) { if (c != a.ctx) memcpy(a.ctx->err, c->err, sizeof c->err); return rc; }
         }
+        if (a.K > 1) RC(pdegpu_lanes_join(a.ctx, a.K));
         return PDEGPU_OK;
     }, &a};
     return pdegpu_graph_run(ctx, &a, sizeof a, body);
@@ -449,21 +454,26 @@ extern "C" int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const 
     Stack dry = {nullptr, 0, 0, true};
     int rc = hs_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
-    if ((rc = pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_hs_2d"))) return rc;
-    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_hs_params P; char *work; int id; };
+    // pairs of a batch run side by side on the context's lanes (one workspace each); a single pair on the context itself
+    const int K = pdegpu_lane_count(ctx, batch);
+    if ((rc = K > 1 ? pdegpu_lanes_prepare(ctx, K, dry.peak, "pdegpu_dev_flow_hs_2d") : pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_hs_2d"))) return rc;
+    struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_hs_params P; char *work; int id, K; };
     Args a;
     memset(&a, 0, sizeof a);                                   // (padding is part of the graph key)
     a.ctx = ctx; a.U = U; a.V = V; a.I0 = I0; a.I1 = I1; a.nrows = nrows; a.ncols = ncols; a.channels = channels; a.batch = batch;
-    a.P = *params; a.work = ctx->work; a.id = 3;
+    a.P = *params; a.work = K > 1 ? ctx->lanes[0]->work : ctx->work; a.id = 3; a.K = K;
     pdegpu_graph_body body = {[](void *p) -> int {
         Args &a = *static_cast<Args *>(p);
         const size_t np = (size_t)a.nrows * a.ncols;
+        if (a.K > 1) RC(pdegpu_lanes_fork(a.ctx, a.K));
         for (int bi = 0; bi < a.batch; bi++) {
-            Stack w = {a.work, 0, 0, false};
-            const int rc = hs_run(a.ctx, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
+            pdegpu_ctx *c = a.K > 1 ? a.ctx->lanes[bi % a.K] : a.ctx;
+            Stack w = {c->work, 0, 0, false};
+            const int rc = hs_run(c, w, a.U + bi * np, a.V + bi * np, a.I0 + bi * np * a.channels, a.I1 + bi * np * a.channels,
                                    a.nrows, a.ncols, a.channels, a.P);
-            if (rc) return rc;
+            if (rc) { if (c != a.ctx) memcpy(a.ctx->err, c->err, sizeof c->err); return rc; }
         }
+        if (a.K > 1) RC(pdegpu_lanes_join(a.ctx, a.K));
         return PDEGPU_OK;
     }, &a};
     return pdegpu_graph_run(ctx, &a, sizeof a, body);

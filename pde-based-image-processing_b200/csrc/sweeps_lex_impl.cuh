@@ -36,12 +36,24 @@ struct LexParams {
     float omega;
 };
 
-// exact reciprocal: this path is bound by the chain of dependent operations anyway, and it is the one held to
-// per-sweep agreement with the reference
-__device__ __forceinline__ float lex_rcp(float x) { return __frcp_rn(x); }
+// (the chain of dependent operations per line is what bounds this path: the reciprocal is the approximate one of the
+// zebra kernels unless built with -DPDEGPU_LEX_EXACT_RCP)
+__device__ __forceinline__ float lex_rcp(float x)
+{
+#ifdef PDEGPU_LEX_EXACT_RCP
+    return __frcp_rn(x);
+#else
+    return fast_rcp(x);                                       // MUFU.RCP, 1 ulp: the sweep-by-sweep bar (1e-5) is measured with it
+#endif
+}
+
+// Threads: warp 0 solves the unknown the pass takes first (all lines), warp 1 the second one (flow families; it runs
+// one line behind warp 0: a row of the second unknown needs the NEW first unknown of its own line only), the last warp
+// is the producer. Two chains of dependent line solves overlap instead of one chain of twice the length.
+template <int NUNK> struct LexThreads { static constexpr int value = 32 * (NUNK + 1); };
 
 template <int NUNK, int NN, int MODE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(LexThreads<NUNK>::value)
 lex_pass_kernel(const LexParams p)
 {
     constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
@@ -54,14 +66,15 @@ lex_pass_kernel(const LexParams p)
     const int TP = NUNK * P;                                  // floats per ring entry
     float *ring = smem;
     float *slabs = ring + (size_t)RL * TP;
-    float *sa = slabs + (size_t)KS * NC * P;                  // eliminated rows: spike, super-diagonal, right-hand side
-    float *sb = sa + 32 * Mr, *sd = sb + 32 * Mr;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sd + 32 * Mr + ((32 * Mr) & 1));
+    float4 *rowsAll = reinterpret_cast<float4 *>(slabs + (size_t)KS * NC * P);   // per solver warp: eliminated rows (spike, super-diagonal, rhs)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(rowsAll + (size_t)NUNK * 32 * Mr);
     uint64_t *sfull = bars, *sempty = bars + KS, *rfull = bars + 2 * KS, *rempty = bars + 2 * KS + RL;
+    unsigned *first_done = reinterpret_cast<unsigned *>(bars + 2 * KS + 2 * RL);   // lines the first solver warp has finished
 
     if (threadIdx.x == 0) {
-        for (int k = 0; k < KS; k++) { mbar_init(&sfull[k], 1); mbar_init(&sempty[k], 1); }
-        for (int k = 0; k < RL; k++) { mbar_init(&rfull[k], 1); mbar_init(&rempty[k], 1); }
+        for (int k = 0; k < KS; k++) { mbar_init(&sfull[k], 1); mbar_init(&sempty[k], NUNK); }
+        for (int k = 0; k < RL; k++) { mbar_init(&rfull[k], 1); mbar_init(&rempty[k], NUNK); }
+        *first_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -70,7 +83,7 @@ lex_pass_kernel(const LexParams p)
     const float *coef = p.coef + pb * NC * P;
     float *tg = p.t + pb * TP;
 
-    if (warp == 1) {
+    if (warp == NUNK) {
         // ======================================= producer =======================================
         if (lane == 0) {
             const unsigned sbytes = (unsigned)(NC * P) * 4u, tbytes = (unsigned)TP * 4u;
@@ -97,10 +110,15 @@ lex_pass_kernel(const LexParams p)
         return;
     }
 
-    // ========================================= solver warp =========================================
+    // ========================================= solver warps =========================================
+    const int q = warp;                                       // 0: the unknown solved first, 1: the second
+    const bool last_solver = q == NUNK - 1;                   // writes the finished line back
+    float4 *rows = rowsAll + (size_t)q * 32 * Mr;
     const float omega = p.omega, om1 = 1.0f - p.omega;
     const int o = lane * Mr;
     const int t0 = (NUNK == 2 ? p.q0 : 0) * P, t1 = (NUNK == 2 ? (p.q0 ^ 1) : 0) * P;
+    const int tq = q == 0 ? t0 : t1, tother = q == 0 ? t1 : t0;
+    const int cq = rC + 3 * q, dq = rD + 3 * q;
     for (int j = 0; j < nlines; j++) {
         const int ks = j % KS, rs = j % RL;
         const bool eLo = j > 0, eHi = j + 1 < nlines;
@@ -112,110 +130,112 @@ lex_pass_kernel(const LexParams p)
         mbar_wait(&sfull[ks], (unsigned)(j / KS) & 1u);
         mbar_wait(&rfull[rs], (unsigned)(j / RL) & 1u);
         if (eHi) mbar_wait(&rfull[(j + 1) % RL], (unsigned)((j + 1) / RL) & 1u);
+        if (NUNK == 2 && q == 1) warp_wait_ge(first_done, (unsigned)j + 1, lane);     // the new first unknown of this line
         if (relaxed) {
-#pragma unroll 1
-            for (int q = 0; q < NUNK; q++) {
-                const int tq = q == 0 ? t0 : t1, tother = q == 0 ? t1 : t0;
-                const int cq = rC + 3 * q, dq = rD + 3 * q;
-                // ---- rows + local forward elimination: afterwards row k reads  x_k + sb*x_{k+1} + sa*x_left = sd
-                float ap = 0.f, bp = 0.f, dp = 0.f;
+            // ---- rows + local forward elimination: afterwards row k reads  x_k + .y*x_{k+1} + .x*x_left = .z
+            float ap = 0.f, bp = 0.f, dp = 0.f;
 #pragma unroll 2
-                for (int k = 0; k < Mr; k++) {
-                    const int e = o + k;
-                    const bool ok = e < n;
-                    const int ec = ok ? e : n - 1;
-                    const bool eP = ec > 0, eN = ec < n - 1;
-                    const float wpr = sl[rWP * P + ec], wnr = sl[rWN * P + ec];
-                    const float wp = eP ? wpr : 0.f, wn = eN ? wnr : 0.f;
-                    const float wl = eLo ? sl[rWL * P + ec] : 0.f, wh = eHi ? sl[rWH * P + ec] : 0.f;
-                    float sw = (wl + wh) + (wp + wn);
-                    float cr = wl * lo[tq + ec] + wh * hi[tq + ec];
-                    float quirk = 0.f;
-                    if (NN == 8) {
-                        const int em = eP ? ec - 1 : ec, ep = eN ? ec + 1 : ec;
-                        const float rlp = sl[(rDG + 0) * P + ec], rln = sl[(rDG + 1) * P + ec];
-                        const float rhp = sl[(rDG + 2) * P + ec], rhn = sl[(rDG + 3) * P + ec];
-                        const float wlp = (eLo && eP) ? rlp : 0.f, wln = (eLo && eN) ? rln : 0.f;
-                        const float whp = (eHi && eP) ? rhp : 0.f, whn = (eHi && eN) ? rhn : 0.f;
-                        sw += (wlp + wln) + (whp + whn);
-                        cr += (wlp * lo[tq + em] + wln * lo[tq + ep]) + (whp * hi[tq + em] + whn * hi[tq + ep]);
-                        // NaN-TRACE diagonal of pdeSolvers.c:1179, see sweeps_tline_impl.cuh
-                        if (MODE == 1) quirk = ((wpr + wnr) + (sl[rWL * P + ec] + sl[rWH * P + ec])) + ((rlp + rlp) + ((p.q0 ? rhp : rln) + rhn));
-                    }
-                    const float C = sl[cq * P + ec], Dd = sl[dq * P + ec];
-                    float bb, dd;
-                    if (MODE == 1) {
-                        const bool has = !is_nan(Dd);
-                        bb = has ? Dd : (NN == 8 ? quirk : sw);
-                        dd = has ? cr + C : cr;
-                    } else {
-                        const bool has = !is_nan(C);
-                        bb = has ? sw + Dd : sw;
-                        float t = C;
-                        if (NUNK == 2) t -= sl[rMM * P + ec] * own[tother + ec];     // the other unknown as it is NOW (old in the
-                        dd = has ? cr + t : cr;                                     // first solve, new in the second)
-                    }
-                    const float a = ok ? -wp : 0.f, c = ok ? -wn : 0.f;
-                    const float b = ok ? bb : 1.0f, d = ok ? dd : 0.f;
-                    const float inv = lex_rcp(k == 0 ? b : b - a * bp);
-                    const float an = k == 0 ? a * inv : (-a * ap) * inv;
-                    const float dn = k == 0 ? d * inv : (d - a * dp) * inv;
-                    bp = c * inv; ap = an; dp = dn;
-                    sa[e] = ap; sb[e] = bp; sd[e] = dp;
+            for (int k = 0; k < Mr; k++) {
+                const int e = o + k;
+                const bool ok = e < n;
+                const int ec = ok ? e : n - 1;
+                const bool eP = ec > 0, eN = ec < n - 1;
+                const float wpr = sl[rWP * P + ec], wnr = sl[rWN * P + ec];
+                const float wp = eP ? wpr : 0.f, wn = eN ? wnr : 0.f;
+                const float wl = eLo ? sl[rWL * P + ec] : 0.f, wh = eHi ? sl[rWH * P + ec] : 0.f;
+                float sw = (wl + wh) + (wp + wn);
+                float cr = wl * lo[tq + ec] + wh * hi[tq + ec];
+                float quirk = 0.f;
+                if (NN == 8) {
+                    const int em = eP ? ec - 1 : ec, ep = eN ? ec + 1 : ec;
+                    const float rlp = sl[(rDG + 0) * P + ec], rln = sl[(rDG + 1) * P + ec];
+                    const float rhp = sl[(rDG + 2) * P + ec], rhn = sl[(rDG + 3) * P + ec];
+                    const float wlp = (eLo && eP) ? rlp : 0.f, wln = (eLo && eN) ? rln : 0.f;
+                    const float whp = (eHi && eP) ? rhp : 0.f, whn = (eHi && eN) ? rhn : 0.f;
+                    sw += (wlp + wln) + (whp + whn);
+                    cr += (wlp * lo[tq + em] + wln * lo[tq + ep]) + (whp * hi[tq + em] + whn * hi[tq + ep]);
+                    // NaN-TRACE diagonal of pdeSolvers.c:1179, see sweeps_tline_impl.cuh
+                    if (MODE == 1) quirk = ((wpr + wnr) + (sl[rWL * P + ec] + sl[rWH * P + ec])) + ((rlp + rlp) + ((p.q0 ? rhp : rln) + rhn));
                 }
-                // ---- first unknown of the chunk in terms of the last one and x_left
-                float Af, Bf, Gf;
-                if (Mr == 1) { Af = 0.f; Bf = -1.0f; Gf = 0.f; }
-                else {
-                    Af = sd[o + Mr - 2]; Bf = sb[o + Mr - 2]; Gf = sa[o + Mr - 2];
-                    for (int r = Mr - 3; r >= 0; r--) {
-                        const float br = sb[o + r];
-                        Af = sd[o + r] - br * Af;
-                        Bf = -br * Bf;
-                        Gf = sa[o + r] - br * Gf;
-                    }
+                const float C = sl[cq * P + ec], Dd = sl[dq * P + ec];
+                float bb, dd;
+                if (MODE == 1) {
+                    const bool has = !is_nan(Dd);
+                    bb = has ? Dd : (NN == 8 ? quirk : sw);
+                    dd = has ? cr + C : cr;
+                } else {
+                    const bool has = !is_nan(C);
+                    bb = has ? sw + Dd : sw;
+                    float t = C;
+                    if (NUNK == 2) t -= sl[rMM * P + ec] * own[tother + ec];     // the other unknown as it is NOW: old for the
+                    dd = has ? cr + t : cr;                                     // first solver, new for the second
                 }
-                // ---- interface system in the lanes' last unknowns, parallel cyclic reduction
-                float An = __shfl_down_sync(FULL, Af, 1), Bn = __shfl_down_sync(FULL, Bf, 1), Gn = __shfl_down_sync(FULL, Gf, 1);
-                if (lane == 31) { An = 0.f; Bn = 0.f; Gn = 0.f; }
-                float al = ap, be = 1.0f - bp * Gn, ga = -bp * Bn, de = dp - bp * An;
-#pragma unroll
-                for (int st = 1; st < 32; st <<= 1) {
-                    float alm = __shfl_up_sync(FULL, al, st), bem = __shfl_up_sync(FULL, be, st);
-                    float gam = __shfl_up_sync(FULL, ga, st), dem = __shfl_up_sync(FULL, de, st);
-                    float alp = __shfl_down_sync(FULL, al, st), bep = __shfl_down_sync(FULL, be, st);
-                    float gap = __shfl_down_sync(FULL, ga, st), dep = __shfl_down_sync(FULL, de, st);
-                    if (lane < st)      { alm = 0.f; bem = 1.0f; gam = 0.f; dem = 0.f; }
-                    if (lane + st > 31) { alp = 0.f; bep = 1.0f; gap = 0.f; dep = 0.f; }
-                    const float k1 = al * lex_rcp(bem), k2 = ga * lex_rcp(bep);
-                    be = be - gam * k1 - alp * k2;
-                    de = de - dem * k1 - dep * k2;
-                    al = -alm * k1;
-                    ga = -gap * k2;
-                }
-                const float l = de * lex_rcp(be);
-                float L = __shfl_up_sync(FULL, l, 1);
-                if (lane == 0) L = 0.f;
-                // ---- local back substitution + SOR, in place in the ring
-                float x = l;
-                for (int r = Mr - 1; r >= 0; r--) {
-                    const int e = o + r;
-                    if (r < Mr - 1) x = sd[e] - sb[e] * x - sa[e] * L;
-                    if (e < n) own[tq + e] = omega * x + om1 * own[tq + e];
-                }
-                __syncwarp();
+                const float a = ok ? -wp : 0.f, c = ok ? -wn : 0.f;
+                const float b = ok ? bb : 1.0f, d = ok ? dd : 0.f;
+                const float inv = lex_rcp(k == 0 ? b : b - a * bp);
+                const float an = k == 0 ? a * inv : (-a * ap) * inv;
+                const float dn = k == 0 ? d * inv : (d - a * dp) * inv;
+                bp = c * inv; ap = an; dp = dn;
+                rows[e] = make_float4(ap, bp, dp, 0.f);
             }
+            // ---- first unknown of the chunk in terms of the last one and x_left
+            float Af, Bf, Gf;
+            if (Mr == 1) { Af = 0.f; Bf = -1.0f; Gf = 0.f; }
+            else {
+                const float4 r0 = rows[o + Mr - 2];
+                Af = r0.z; Bf = r0.y; Gf = r0.x;
+                for (int r = Mr - 3; r >= 0; r--) {
+                    const float4 rr = rows[o + r];
+                    Af = rr.z - rr.y * Af;
+                    Bf = -rr.y * Bf;
+                    Gf = rr.x - rr.y * Gf;
+                }
+            }
+            // ---- interface system in the lanes' last unknowns, parallel cyclic reduction
+            float An = __shfl_down_sync(FULL, Af, 1), Bn = __shfl_down_sync(FULL, Bf, 1), Gn = __shfl_down_sync(FULL, Gf, 1);
+            if (lane == 31) { An = 0.f; Bn = 0.f; Gn = 0.f; }
+            float al = ap, be = 1.0f - bp * Gn, ga = -bp * Bn, de = dp - bp * An;
+#pragma unroll
+            for (int st = 1; st < 32; st <<= 1) {
+                float alm = __shfl_up_sync(FULL, al, st), bem = __shfl_up_sync(FULL, be, st);
+                float gam = __shfl_up_sync(FULL, ga, st), dem = __shfl_up_sync(FULL, de, st);
+                float alp = __shfl_down_sync(FULL, al, st), bep = __shfl_down_sync(FULL, be, st);
+                float gap = __shfl_down_sync(FULL, ga, st), dep = __shfl_down_sync(FULL, de, st);
+                if (lane < st)      { alm = 0.f; bem = 1.0f; gam = 0.f; dem = 0.f; }
+                if (lane + st > 31) { alp = 0.f; bep = 1.0f; gap = 0.f; dep = 0.f; }
+                const float k1 = al * lex_rcp(bem), k2 = ga * lex_rcp(bep);
+                be = be - gam * k1 - alp * k2;
+                de = de - dem * k1 - dep * k2;
+                al = -alm * k1;
+                ga = -gap * k2;
+            }
+            const float l = de * lex_rcp(be);
+            float L = __shfl_up_sync(FULL, l, 1);
+            if (lane == 0) L = 0.f;
+            // ---- local back substitution + SOR, in place in the ring
+            float x = l;
+            for (int r = Mr - 1; r >= 0; r--) {
+                const int e = o + r;
+                if (r < Mr - 1) { const float4 rr = rows[e]; x = rr.z - rr.y * x - rr.x * L; }
+                if (e < n) own[tq + e] = omega * x + om1 * own[tq + e];
+            }
+        }
+        __syncwarp();
+        if (NUNK == 2 && q == 0) {
+            if (lane == 0) { __threadfence_block(); st_release(first_done, (unsigned)j + 1); }
+        }
+        if (last_solver && relaxed) {
             // the relaxed line back to global memory (pads are never touched: they stay as the preparation wrote them)
             for (int qq = 0; qq < NUNK; qq++) {
                 const float4 *s4 = reinterpret_cast<const float4 *>(own + qq * P);
                 float4 *g4 = reinterpret_cast<float4 *>(tg + (long long)j * TP + qq * P);
                 for (int e = lane; e < (P >> 2); e += 32) g4[e] = s4[e];
             }
+            __syncwarp();
         }
-        __syncwarp();
         if (lane == 0) {
             mbar_arrive(&sempty[ks]);
-            if (eLo) mbar_arrive(&rempty[(j - 1) % RL]);     // line j-1 has served its last reader
+            if (eLo) mbar_arrive(&rempty[(j - 1) % RL]);     // line j-1 has served this warp's last reader
         }
     }
 }

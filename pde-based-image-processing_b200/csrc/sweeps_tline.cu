@@ -482,8 +482,8 @@ static bool lex_geometry(int n, int nunk, int nc, LexGeom &g)
     const int P = (n + 3) & ~3;
     g.Mr = ((n + 31) / 32) | 1;
     const size_t room = 227 * 1024;
-    const size_t slab = (size_t)nc * P * 4, line = (size_t)nunk * P * 4, scratch = (size_t)3 * 32 * g.Mr * 4;
-    const int cand[][2] = {{2, 4}, {2, 3}, {1, 4}, {1, 3}};
+    const size_t slab = (size_t)nc * P * 4, line = (size_t)nunk * P * 4, scratch = (size_t)nunk * 32 * g.Mr * 16;
+    const int cand[][2] = {{2, 5}, {2, 4}, {2, 3}, {1, 4}, {1, 3}};
     for (auto &c : cand) {
         const size_t need = c[0] * slab + c[1] * line + scratch + (size_t)(2 * c[0] + 2 * c[1]) * 8 + 128;
         if (need <= room) { g.KS = c[0]; g.RL = c[1]; g.smem = need; return true; }
@@ -501,7 +501,7 @@ int lex_pass(pdegpu_ctx *ctx, LexParams &p, int batch, double bytes, const char 
     cudaError_t e = cudaFuncSetAttribute(lex_pass_kernel<NUNK, NN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(lex_pass_kernel)");
     PDEGPU_PROF(ctx, name, bytes);
-    lex_pass_kernel<NUNK, NN, MODE><<<batch, 64, g.smem, ctx->stream>>>(p);
+    lex_pass_kernel<NUNK, NN, MODE><<<batch, LexThreads<NUNK>::value, g.smem, ctx->stream>>>(p);
     PDEGPU_LAUNCH_CHECK(ctx, "lex_pass_kernel");
     return PDEGPU_OK;
 }

@@ -22,5 +22,8 @@ pdegpu_ctx *gw_ctx(const char *gw)
         }
         mexAtExit(gw_ctx_release);
     }
+    /* the sweep order follows the environment at EVERY call: setenv('PDEGPU_ORDER', 'reference') in a running Matlab /
+     * Octave session switches the unchanged drivers to the reference's line order (include/pdegpu.h) */
+    pdegpu_set_sweep_order(g_ctx, pdegpu_order_from_env());
     return g_ctx;
 }

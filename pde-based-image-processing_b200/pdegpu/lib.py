@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBPATH = os.environ.get("PDEGPU_LIB") or os.path.join(os.path.dirname(_HERE), "libpdegpu.so")
 
 FLOW_ELIN4, FLOW_LLIN4, FLOW_LLIN8, DISP_LLIN4, PDE4, PDE8 = range(6)
-ORDER_FAST, ORDER_REFERENCE = 0, 1
+ORDER_FAST, ORDER_REFERENCE, ORDER_AUTO = 0, 1, 2
 W_W, W_N, W_E, W_S, W_NW, W_NE, W_SE, W_SW = range(8)
 
 OK = 0

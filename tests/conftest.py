@@ -12,6 +12,11 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 
+# The suites written against the zebra / red-black kernels (generation cross-checks, throughput-shaped properties) pin
+# that order; tests/test_gpu_reference_order.py switches to "reference" / "auto" explicitly.
+os.environ.setdefault("PDEGPU_ORDER", "fast")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
 

@@ -151,6 +151,24 @@ def test_fmg_batch_equals_single(ctx):
         assert np.array_equal(U1, Ub[k]) and np.array_equal(V1, Vb[k])
 
 
+@pytest.mark.parametrize("driver", ["fmg", "hs"])
+def test_pairs_on_parallel_lanes_equal_single_pairs(built, driver):
+    """the pairs of a batch run side by side on the context's lanes (child streams with their own workspace, one branch
+    per lane in the captured graph): direct run, capture and replay of a batch of 5 must all equal the pairs run alone"""
+    from pdegpu import lib
+    c = lib.Context(0)
+    nr, nc = 72, 88
+    ps = [small_pair(30 + k, nr, nc, 1) for k in range(5)]
+    I0 = np.stack([p[0] for p in ps]); I1 = np.stack([p[1] for p in ps])
+    fn = c.flow_fmg if driver == "fmg" else c.flow_hs
+    single = [fn(p[0], p[1]) for p in ps]
+    for _ in range(3):
+        Ub, Vb = fn(I0, I1)
+        for k in range(5):
+            assert np.array_equal(single[k][0], Ub[k]) and np.array_equal(single[k][1], Vb[k])
+    c.close()
+
+
 # ---- FlowEminHS_elin_2D_v10 (BASELINE configs[0]): Horn-Schunck, one linear solve per pyramid level ----
 @pytest.mark.parametrize("C", [1, 3])
 def test_hs_converged_solves_match_reference(ctx, C):
