@@ -280,10 +280,13 @@ def fas_rhs(R, A, gd):
     return ((np.asarray(R, dtype=F32) + np.asarray(A, dtype=F32)) / np.asarray(gd, dtype=F32)).astype(F32)
 
 
-def ad_diff_weights(D, quantile=0.5):
+def ad_diff_weights(D, quantile=0.5, flow_variant=False):
     """ADdiffWeights, matlab/denoising/TVdenoise8.m:119-231 (Alvarez derivatives, lambda = the `quantile`
     order statistic of the non-zero squared gradient norms). Double precision.
-    Returns (W, NW, N, NE, E, SE, S, SW), each rows x cols."""
+    flow_variant: the copy in matlab/optical_flow/FlowEminAD_llin_2D_v10.m:416-488 -- the order statistic is
+    round(numel*quantile) without the eps (:459) and the weights towards the missing neighbours of border pixels are
+    NOT zeroed (:472-479; the line solvers never read them).
+    Returns (W, NW, N, NE, E, SE, S, SW, lambda), each rows x cols."""
     D = np.asarray(D, dtype=np.float64)
     if D.ndim == 2:
         D = D[:, :, None]
@@ -302,7 +305,7 @@ def ad_diff_weights(D, quantile=0.5):
     srt = np.sort(nrm.reshape(-1, order="F"))
     srt = srt[srt != 0]
     if srt.size:
-        k = int(np.floor(srt.size * quantile + np.finfo(np.float64).eps + 0.5))   # Matlab round()
+        k = int(np.floor(srt.size * quantile + (0.0 if flow_variant else np.finfo(np.float64).eps) + 0.5))   # Matlab round()
         lam = srt[k - 1]
     else:
         lam = 1.0
@@ -312,6 +315,9 @@ def ad_diff_weights(D, quantile=0.5):
     def cs(a, dr, dc):
         return np.roll(np.roll(a, dr, axis=0), dc, axis=1)
 
+    if flow_variant:
+        return (0.5 * (dyy + cs(dyy, 0, 1)), 0.25 * (dxy + cs(dxy, 1, 1)), 0.5 * (dxx + cs(dxx, 1, 0)), -0.25 * (dxy + cs(dxy, 1, -1)),
+                0.5 * (dyy + cs(dyy, 0, -1)), 0.25 * (dxy + cs(dxy, -1, -1)), 0.5 * (dxx + cs(dxx, -1, 0)), -0.25 * (dxy + cs(dxy, -1, 1)), lam)
     W = 0.5 * (dyy + cs(dyy, 0, 1));      W[:, 0] = 0
     NW = 0.25 * (dxy + cs(dxy, 1, 1));    NW[:, 0] = 0;   NW[0, :] = 0
     N = 0.5 * (dxx + cs(dxx, 1, 0));      N[0, :] = 0
@@ -418,3 +424,62 @@ def interp2_rows(Vals, Xq):
 def round_uint8(A):
     """class uint8 after a toolbox call (imresize, imfilter on uint8 images): round half away from zero, saturate."""
     return np.clip(np.floor(np.asarray(A, dtype=np.float64) + 0.5), 0, 255).astype(F32)
+
+
+def tv4_diff_weights(D):
+    """DiffWeights of matlab/denoising/TVdenoise4.m:116-148: the 4-neighbour edge weights of OPdiffWeights for ONE
+    field with several frames, maximum over the frames (:131-134), outward border edges zeroed (:145-148). Computed in the class of D (single for the images
+    runme.m:143 passes): one rounding per operation. Returns (wW, wN, wE, wS), rows x cols."""
+    D = np.asarray(D, dtype=F32)
+    if D.ndim == 2:
+        D = D[:, :, None]
+    q = np.array([[0.25, 0.0, -0.25]])
+    Dver = np.stack([imfilter(D[:, :, k], q.T, "replicate") for k in range(D.shape[2])], axis=2).astype(F32)
+    Dhor = np.stack([imfilter(D[:, :, k], q, "replicate") for k in range(D.shape[2])], axis=2).astype(F32)
+
+    def cs(a, dr, dc):
+        return np.roll(np.roll(a, dr, axis=0), dc, axis=1)
+
+    def edge(dr, dc, G):
+        a = (cs(D, dr, dc) - D).astype(F32); b = (G + cs(G, dr, dc)).astype(F32)
+        return ((a * a).astype(F32) + (b * b).astype(F32)).astype(F32).max(axis=2)
+
+    wW, wE = edge(0, 1, Dver), edge(0, -1, Dver)
+    wN, wS = edge(1, 0, Dhor), edge(-1, 0, Dhor)
+    f = lambda w: (F32(1) / np.sqrt((w + F32(0.00001)).astype(F32))).astype(F32)
+    wW, wN, wE, wS = f(wW), f(wN), f(wE), f(wS)
+    wW[:, 0] = 0; wE[:, -1] = 0; wN[0, :] = 0; wS[-1, :] = 0                # :145-148: no edge leaves the image
+    return wW, wN, wE, wS
+
+
+def disp_terms(d1, d2, dU, b1, b2, alpha, gradmag):
+    """Robust weights and channel sums of matlab/disparity/DispEminND_llin_2D.m:251-280 (single precision; plain sum over
+    the channels, :279-280: a NaN of a warped pixel reaches CuGd / DuGd). d1 = (I1dt, I1dx, I1dy); d2 = None, the three
+    first derivatives or the five second derivatives (gradmag). Returns (CuGd, DuGd)."""
+    dU = np.asarray(dU, dtype=F32)[:, :, None]
+    I1dt, I1dx = d1[0], d1[1]
+    r = (I1dt - (I1dx * dU).astype(F32)).astype(F32)
+    g1 = (F32(b1) / (F32(alpha) * np.sqrt(((r * r).astype(F32) + F32(0.00001)).astype(F32))).astype(F32)).astype(F32)
+    Cu = [((I1dt * I1dx).astype(F32) * g1).astype(F32)]
+    Du = [((I1dx * I1dx).astype(F32) * g1).astype(F32)]
+    if d2 is not None:
+        if gradmag:
+            xt, yt, xx, _, xy = d2
+            n2 = (((xt - (xx * dU).astype(F32)).astype(F32) ** 2).astype(F32) + ((yt - (xy * dU).astype(F32)).astype(F32) ** 2).astype(F32)).astype(F32)
+            c2 = ((xt * xx).astype(F32) + (yt * xy).astype(F32)).astype(F32)
+            e2 = ((xx * xx).astype(F32) + (xy * xy).astype(F32)).astype(F32)
+        else:
+            t, x = d2[0], d2[1]
+            n2 = ((t - (x * dU).astype(F32)).astype(F32) ** 2).astype(F32)
+            c2, e2 = (t * x).astype(F32), (x * x).astype(F32)
+        g2 = (F32(b2) / (F32(alpha) * np.sqrt((n2 + F32(0.00001)).astype(F32))).astype(F32)).astype(F32)
+        Cu.append((c2 * g2).astype(F32)); Du.append((e2 * g2).astype(F32))
+
+    def s3(parts):
+        acc = None
+        for p_ in parts:
+            for k in range(p_.shape[2]):
+                acc = p_[:, :, k].copy() if acc is None else (acc + p_[:, :, k]).astype(F32)
+        return acc
+
+    return s3(Cu), s3(Du)

@@ -271,3 +271,143 @@ def disp_sym(Il, Ir, backend, alpha=0.035, beta=0.4, omega=1.9, firstLoop=3, sec
             U0 = ms.imresize_bilinear((U0 * up).astype(F32), output_size=size)
             U1 = ms.imresize_bilinear((U1 * up).astype(F32), output_size=size)
     return U0, U1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sibling drivers runme.m also calls: same gateways, other Matlab glue
+# ------------------------------------------------------------------------------------------------------------------
+def tvdenoise4(I_in, backend, alpha=5.0, omega=1.75, outer_iter=10, inner_iter=5, solver=2, scl=0.5, scl_factor=0.75):
+    """Iout = TVdenoise4(I_in), matlab/denoising/TVdenoise4.m:36-112: multi-scale lagged-diffusivity TV denoising with
+    the 4-neighbour weights of its own DiffWeights (:116) and PDEsolver4. I_in: rows x cols (x frames), single."""
+    I_in = np.asarray(I_in, dtype=F32)
+    shape = I_in.shape
+    I0 = I_in.reshape(shape[0], shape[1], -1)
+    ds_rows, ds_cols = math.ceil(shape[0] * scl), math.ceil(shape[1] * scl)                            # :52-53
+    G = ms.fspecial_gaussian(7, 2.0)                                                                    # :57
+    Iin = [I0]
+    while True:                                                                                         # :61-77
+        nxt = ms.imresize_bilinear(Iin[-1], scale=scl_factor)
+        Iin[-1] = ms.imfilter(Iin[-1], G)
+        Iin.append(nxt)
+        if nxt.shape[0] <= ds_rows or nxt.shape[1] <= ds_cols:
+            Iin[-1] = ms.imfilter(Iin[-1], G)
+            break
+    Iout = Iin[-1].copy()                                                                               # :78
+    eps = F32(np.finfo(np.float64).eps)
+    for s in range(len(Iin) - 1, -1, -1):                                                               # :80
+        for _ in range(outer_iter + 1):                                                                 # :82  iter = 0:outer_iter
+            df = (Iout - Iin[s]).astype(F32)
+            psi = (F32(1) / np.sqrt(((df * df).astype(F32) + eps).astype(F32))).astype(F32)             # :84
+            wW, wN, wE, wS = ms.tv4_diff_weights(Iout)                                                  # :85
+            sw = (((wW + wN).astype(F32) + wE).astype(F32) + wS).astype(F32)
+            TRACE = (psi + (F32(alpha) * sw).astype(F32)[:, :, None]).astype(F32)                       # :87
+            B = (psi * Iin[s]).astype(F32)                                                              # :88
+            fr = Iout.shape[2]
+            aw = [np.repeat((F32(alpha) * w).astype(F32)[:, :, None], fr, axis=2) for w in (wW, wN, wE, wS)]
+            Iout = backend.call("PDEsolver4", [Iout, TRACE, B] + aw + [F32(inner_iter), F32(omega), F32(solver)], 1)[0]   # :90-99
+            Iout = np.asarray(Iout, dtype=F32).reshape(Iin[s].shape)
+        if s > 0:                                                                                       # :108-110
+            Iout = ms.imresize_bilinear(Iout, output_size=Iin[s - 1].shape[:2])
+    return Iout.reshape(shape)
+
+
+def disp_llin(Il, Ir, backend, alpha=0.042, omega=1.9, firstLoop=4, secondLoop=6, iter=4, b1=1.48, b2=0.29, scl_factor=0.75,
+              solver=2, fst_grad=True, snd_term="gradmag", max_scales=None, oob=np.nan):
+    """U = DispEminND_llin_2D(Il, Ir, fstTerm, sndTerm) as runme.m:20 calls it ('grad', 'gradmag'): late-linearisation
+    stereo with ONE disparity field, DdiffWeights and Disp_sor_llin4_2d. Il, Ir: rows x cols x channels, 0..255.
+    matlab/disparity/DispEminND_llin_2D.m, line numbers in the comments (spatial a-priori inputs omitted)."""
+    I0 = (np.asarray(Il, dtype=F32).reshape(Il.shape[0], Il.shape[1], -1) / F32(255)).astype(F32)      # :74-75
+    I1 = (np.asarray(Ir, dtype=F32).reshape(Ir.shape[0], Ir.shape[1], -1) / F32(255)).astype(F32)
+    G = ms.fspecial_gaussian(5, 1.25)                                                                   # :98
+    It0, It1 = [I0], [I1]
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :106-125
+        n0, n1 = ms.imresize_bilinear(It0[-1], scale=scl_factor), ms.imresize_bilinear(It1[-1], scale=scl_factor)
+        It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+        It0.append(n0); It1.append(n1)
+        if n0.shape[0] <= 10 or n0.shape[1] <= 10:
+            It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+            break
+    S = len(It0)
+    F0 = [ms.rgb2grad(x) if fst_grad else x for x in It0]                                               # :130-143
+    F1 = [ms.rgb2grad(x) if fst_grad else x for x in It1]
+    U = None
+    for s in range(S - 1, -1, -1):                                                                      # :184
+        rows, cols = It0[s].shape[:2]
+        Xg, Yg = np.meshgrid(np.arange(1, cols + 1, dtype=F32), np.arange(1, rows + 1, dtype=F32))
+        if U is None:
+            U = np.zeros((rows, cols), F32)
+        for _ in range(firstLoop):                                                                      # :207
+            X = (Xg + U).astype(F32)
+            W1 = backend.bilin(F1[s], X, Yg, oob)                                                       # :212
+            d1 = backend.call("FstDerivatives5", [F0[s], W1], 3)                                        # :224
+            d2 = None
+            if snd_term != "none":
+                W2 = backend.bilin(It1[s], X, Yg, oob)                                                  # :218
+                d2 = backend.call("SndDerivatives5", [It0[s], W2], 5) if snd_term == "gradmag" else \
+                    backend.call("FstDerivatives5", [It0[s], W2], 3)                                    # :233,237
+            dU = np.zeros((rows, cols), F32)
+            for _ in range(secondLoop):                                                                 # :254
+                CuGd, DuGd = ms.disp_terms(d1, d2, dU, b1, b2, alpha, snd_term == "gradmag")            # :259-280
+                w = backend.call("DdiffWeights", [(U + dU).astype(F32), F32(0.00001)], 4)               # :277  [wW wN wE wS]
+                dU = backend.call("Disp_sor_llin4_2d", [U, dU, CuGd, DuGd] + list(w) + [F32(iter), F32(omega), F32(solver)], 1)[0]   # :285-296
+            U = ms.medfilt2_symmetric((U + dU).astype(F32))                                             # :303
+        if s > 0:                                                                                       # :313-315
+            U = ms.imresize_bilinear((U * F32(1.0 / scl_factor)).astype(F32), output_size=It0[s - 1].shape[:2])
+    return U
+
+
+def flow_ad(I0, I1, backend, quantile=0.9, diffusion="image", alpha=0.0420, omega=1.9, firstLoop=4, secondLoop=4, iter=4,
+            b1=1.4843, b2=0.2915, scl_factor=0.75, solver=2, fst_grad=True, snd_term="gradmag", max_scales=None, oob=np.nan):
+    """[U V] = FlowEminAD_llin_2D_v10(cat(3, I0, I1), channels, fstTerm, sndTerm, 'diffusion', diffusion) as runme.m:54,64
+    calls it: the late-linearisation flow driver with anisotropic (Nagel-Enkelmann type) diffusion -- 8 edge weights from
+    its own ADdiffWeights (:416-488), computed once per level from the first frame ('image') or per inner iteration from
+    U+dU+V+dV ('flow'), and Oflow_sor_llin8_2d. matlab/optical_flow/FlowEminAD_llin_2D_v10.m, line numbers in the comments."""
+    I0 = (np.asarray(I0, dtype=F32).reshape(I0.shape[0], I0.shape[1], -1) / F32(255)).astype(F32)      # :79
+    I1 = (np.asarray(I1, dtype=F32).reshape(I1.shape[0], I1.shape[1], -1) / F32(255)).astype(F32)
+    G = ms.fspecial_gaussian(5, 1.25)                                                                   # :102
+    It0, It1 = [I0], [I1]
+    scales = max_scales or (1 << 30)
+    while len(It0) < scales:                                                                            # :110-131
+        n0, n1 = ms.imresize_bilinear(It0[-1], scale=scl_factor), ms.imresize_bilinear(It1[-1], scale=scl_factor)
+        It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+        It0.append(n0); It1.append(n1)
+        if n0.shape[0] <= 20 or n0.shape[1] <= 20:
+            It0[-1], It1[-1] = ms.imfilter(It0[-1], G), ms.imfilter(It1[-1], G)
+            break
+    S = len(It0)
+    F0 = [ms.rgb2grad(x) if fst_grad else x for x in It0]
+    F1 = [ms.rgb2grad(x) if fst_grad else x for x in It1]
+    w8 = lambda D: [np.asarray(x, dtype=F32) for x in ms.ad_diff_weights(D, quantile, flow_variant=True)[:8]]   # W NW N NE E SE S SW
+    U = V = None
+    for s in range(S - 1, -1, -1):                                                                      # :198
+        rows, cols = It0[s].shape[:2]
+        Xg, Yg = np.meshgrid(np.arange(1, cols + 1, dtype=F32), np.arange(1, rows + 1, dtype=F32))
+        if diffusion == "image":
+            w = w8(It0[s])                                                                              # :214
+        if U is None:
+            U = np.zeros((rows, cols), F32); V = np.zeros((rows, cols), F32)
+        for _ in range(firstLoop):                                                                      # :233
+            X, Y = (Xg + U).astype(F32), (Yg + V).astype(F32)
+            W1 = backend.bilin(F1[s], X, Y, oob)                                                        # :238
+            d1 = backend.call("FstDerivatives5", [F0[s], W1], 3)
+            d2 = None
+            if snd_term != "none":
+                W2 = backend.bilin(It1[s], X, Y, oob)
+                d2 = backend.call("SndDerivatives5", [It0[s], W2], 5) if snd_term == "gradmag" else \
+                    backend.call("FstDerivatives5", [It0[s], W2], 3)
+            dU = np.zeros((rows, cols), F32); dV = np.zeros((rows, cols), F32)
+            for _ in range(secondLoop):                                                                 # :295
+                if diffusion == "flow":
+                    w = w8((((U + dU).astype(F32) + V).astype(F32) + dV).astype(F32))                   # :343
+                M, Cu, Cv, Du, Dv = ms.llin_terms(d1, d2, dU, dV, b1, b2, alpha, snd_term == "gradmag")  # :305-352 (same formulas)
+                dU, dV = backend.call("Oflow_sor_llin8_2d", [U, V, dU, dV, M, Cu, Cv, Du, Dv] + w +
+                                      [F32(iter), F32(omega), F32(solver)], 2)                          # :357-377
+            U = ms.medfilt2_symmetric((U + dU).astype(F32))                                             # :383-384
+            V = ms.medfilt2_symmetric((V + dV).astype(F32))
+        if s > 0:                                                                                       # :393-396
+            up = F32(1.0 / scl_factor)
+            size = It0[s - 1].shape[:2]
+            U = ms.imresize_bilinear((U * up).astype(F32), output_size=size)
+            V = ms.imresize_bilinear((V * up).astype(F32), output_size=size)
+    return U, V

@@ -51,6 +51,12 @@ class GpuBackend:
     def call(self, fn: str, args: Sequence, nlhs: int) -> List[np.ndarray]:
         return call(fn, args, nlhs)
 
+    def bilin(self, Iin, X, Y, oob: float) -> np.ndarray:
+        """BilinInterp_2d as the drivers call it; the gateway passes NaN for out-of-image pixels"""
+        if not np.isnan(oob):
+            raise ValueError("the BilinInterp_2d gateway marks out-of-image pixels with NaN")
+        return call("BilinInterp_2d", [np.asarray(Iin, dtype=np.float32), np.asarray(X, dtype=np.float32), np.asarray(Y, dtype=np.float32)], 1)[0]
+
 
 def _make(fn: str, default_nargout: int):
     def f(*args, nargout: int = default_nargout):

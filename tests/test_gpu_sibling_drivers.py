@@ -1,0 +1,77 @@
+"""The sibling drivers runme.m also calls: TVdenoise4 (runme.m:143), DispEminND_llin_2D (runme.m:20),
+FlowEminAD_llin_2D_v10 with 'diffusion' = 'image' and 'flow' (runme.m:54,64). They use the same MEX gateways as the
+drivers with a device pipeline, so the drop-in claim for them is: THE UNCHANGED DRIVER, run on libpdegpu's gateways,
+gives what it gives on the reference's MEX files. The driver text is restated once (oracle/pipelines.py, the stand-in for
+the Matlab interpreter, CPU-checked in tests/test_oracle_pipelines.py) and run twice: every MEX call through the
+gateways -> C ABI -> CUDA, and every MEX call through the unmodified reference.
+
+  * in the reference's line order (PDEGPU_ORDER=reference) at the drivers' DEFAULT parameters: <= 1e-3 px / 1e-3 of the
+    image range, identical NaN pattern;
+  * in the default (zebra) order at the defaults: the same quality against the ground truth."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pipelines
+from pdegpu import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref():
+    from oracle import oracle as o
+    return o.RefBackend() if o.have_ref() else o.OracleBackend()
+
+
+@pytest.fixture(params=["reference", "fast"])
+def order(request):
+    os.environ["PDEGPU_ORDER"] = request.param
+    yield request.param
+    os.environ["PDEGPU_ORDER"] = "fast"
+
+
+def test_tvdenoise4_on_the_gateways(gpu, order):
+    rng = np.random.default_rng(8)
+    nr, nc = 96, 120
+    ii, jj = np.meshgrid(np.arange(nr), np.arange(nc), indexing="ij")
+    clean = np.stack([0.5 + 0.3 * np.sin(ii / 17.0) * np.cos(jj / 23.0), 0.4 + 0.2 * np.cos(ii / 11.0)], axis=2).astype(np.float32)
+    noisy = (clean + 0.08 * rng.standard_normal(clean.shape)).astype(np.float32)
+    g = pipelines.tvdenoise4(noisy, gpu, outer_iter=5)
+    o = pipelines.tvdenoise4(noisy, _ref(), outer_iter=5)
+    rm = lambda a: float(np.sqrt(np.mean((a - clean) ** 2)))
+    assert np.isfinite(g).all() and rm(g) < 0.6 * rm(noisy)
+    if order == "reference":
+        assert float(np.max(np.abs(g - o))) < 1e-3 * float(np.max(np.abs(o)))
+    else:
+        assert abs(rm(g) - rm(o)) < 0.1 * rm(o)
+
+
+def test_disp_llin_on_the_gateways(gpu, order):
+    nr, nc = 96, 128
+    Il, Ir, u, _ = synth.image_pair(45, nr, nc, nframes=3, scale=255.0, max_flow=3.0, horizontal=True)
+    g = pipelines.disp_llin(Il, Ir, gpu)
+    o = pipelines.disp_llin(Il, Ir, _ref())
+    s = (slice(10, -10), slice(10, -10))
+    eg, eo = float(np.nanmean(np.abs(g[s] - u[s]))), float(np.nanmean(np.abs(o[s] - u[s])))
+    assert eg < 0.08
+    if order == "reference":
+        assert np.array_equal(np.isnan(g), np.isnan(o))
+        assert float(np.nanmean(np.abs(g - o))) < 1e-3
+    else:
+        assert abs(eg - eo) < 0.02
+
+
+@pytest.mark.parametrize("diffusion", ["image", "flow"])
+def test_flow_ad_on_the_gateways(gpu, order, diffusion):
+    nr, nc = 96, 128
+    I0, I1, u, v = synth.image_pair(13, nr, nc, nframes=3, scale=255.0, max_flow=2.0)
+    Ug, Vg = pipelines.flow_ad(I0.reshape(nr, nc, 3), I1.reshape(nr, nc, 3), gpu, diffusion=diffusion)
+    Uo, Vo = pipelines.flow_ad(I0.reshape(nr, nc, 3), I1.reshape(nr, nc, 3), _ref(), diffusion=diffusion)
+    s = (slice(8, -8), slice(8, -8))
+    aee = lambda U, V: float(np.mean(np.sqrt((U[s] - u[s]) ** 2 + (V[s] - v[s]) ** 2)))
+    assert np.isfinite(Ug).all() and aee(Ug, Vg) < 0.3
+    if order == "reference":
+        assert float(np.mean(np.sqrt((Ug - Uo) ** 2 + (Vg - Vo) ** 2))) < 1e-3
+    else:
+        assert abs(aee(Ug, Vg) - aee(Uo, Vo)) < 0.03
