@@ -75,8 +75,11 @@ def parse():
                     help="batch: BASELINE configs[1] inner solve on a batch of 640x480 systems (default, the driver's line); "
                          "band: configs[4], ONE band_n x band_n image split into column bands with halo exchange (strong scaling)")
     ap.add_argument("--band-n", type=int, default=16384)
+    ap.add_argument("--band-transport", default="p2p", choices=["p2p", "nccl"], help="--workload band: libpdegpu's peer-memory exchange or NCCL send/recv")
     ap.add_argument("--band-iters", type=int, default=8, help="red-black sweeps per step")
-    ap.add_argument("--band-T", type=int, default=1, help="sweeps per halo exchange (halo = 2T columns)")
+    ap.add_argument("--band-T", type=int, default=4, help="sweeps per halo exchange (halo = 2T columns)")
+    ap.add_argument("--band-leg", type=int, default=1, help="one band-n x band-n image in column bands as a leg of the default line (0 = skip)")
+    ap.add_argument("--batch512", type=int, default=512, help="1080p pairs of the configs[4] batch leg, split over the GPUs (0 = skip)")
     ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
     ap.add_argument("--flow-ref-batch", type=int, default=64, help="640x480 pairs per GPU for the flows/s leg in the reference's line order (0 = skip)")
     ap.add_argument("--sweep-legs", type=int, default=1, help="relaxation sweep alone at 1080p / 4096x2160 / point solver (0 = skip)")
@@ -445,9 +448,17 @@ def device_system(torch, dev, fam, nr, nc, batch, seed):
         f.update({"Cu": -gd * it * ix, "Du": gd * ix * ix})
         f["Cu"][nan] = float("nan"); f["Du"][nan] = float("nan")
         f["U"], f["dU"] = r(-4, 8), r(-0.05, 0.1)
-    else:                                         # pde4: TRACE = sum of weights + data weight, B = data weight * image
+    else:                                         # pde4 / pde8: TRACE = sum of weights + data weight, B = data weight * image
         psi, img = r(0.5, 1.0), r(0, 1)
         f["TRACE"] = f["wW"] + f["wE"] + f["wN"] + f["wS"] + psi
+        if fam == "pde8":                         # small diagonal weights of either sign, edge-symmetric (ADdiffWeights' dxy terms)
+            dg, da = r(-0.1, 0.2), r(-0.1, 0.2)
+            f["wSE"] = dg.clone(); f["wSE"][:, -1, :] = 0; f["wSE"][:, :, -1] = 0
+            f["wNW"] = torch.zeros_like(dg); f["wNW"][:, 1:, 1:] = dg[:, :-1, :-1]
+            f["wNE"] = da.clone(); f["wNE"][:, -1, :] = 0; f["wNE"][:, :, 0] = 0
+            f["wSW"] = torch.zeros_like(da); f["wSW"][:, 1:, :-1] = da[:, :-1, 1:]
+            f["TRACE"] = f["TRACE"] + f["wSE"] + f["wNW"] + f["wNE"] + f["wSW"]
+            del dg, da
         f["TRACE"][nan] = float("nan")
         f["B"] = psi * img
         f["X"] = img + 0.05 * torch.randn(shape, device=dev, generator=g)
@@ -467,6 +478,10 @@ def device_sysd(lib, fam, f, nr, nc, batch):
     if fam == "disp":
         return lib.make_system(lib.DISP_LLIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(),), x0=(f["U"].data_ptr(),),
                                c=(f["Cu"].data_ptr(),), d=(f["Du"].data_ptr(),), w=w), ("dU",)
+    if fam == "pde8":
+        w = w + [f[k].data_ptr() for k in ("wNW", "wNE", "wSE", "wSW")]
+        return lib.make_system(lib.PDE8, nr, nc, batch=batch, batch_stride=n, x=(f["X"].data_ptr(),),
+                               c=(f["B"].data_ptr(),), d=(f["TRACE"].data_ptr(),), w=w), ("X",)
     return lib.make_system(lib.PDE4, nr, nc, batch=batch, batch_stride=n, x=(f["X"].data_ptr(),),
                            c=(f["B"].data_ptr(),), d=(f["TRACE"].data_ptr(),), w=w), ("X",)
 
@@ -476,6 +491,7 @@ SWEEP_LEGS = [
     ("sweep_1080p", "Oflow_sor_elin4_2d (finest level of configs[2], FlowEminNDFASFMG_elin_2D_v10.m:367-464)", "elin4", 1080, 1920, 8, 2, 4, 1.9, 52.0),
     ("sweep_4096x2160", "Disp_sor_llin_sym4_2d = two Disp llin4 systems (finest level of configs[3], DispEminND_llin_sym_2D.m:227-246)", "disp", 2160, 4096, 4, 2, 4, 1.9, 36.0),
     ("sweep_tv_4096x2160", "PDEsolver4 (TVdenoise4.m:85-90 at the configs[3] image size)", "pde4", 2160, 4096, 4, 2, 4, 1.75, 32.0),
+    ("tv8_4096x2160", "PDEsolver8 (TVdenoise8.m:87-100 at the configs[3] image size; ONE line iteration per call, SURVEY Q4)", "pde8", 2160, 4096, 4, 2, 1, 1.75, 48.0),
     ("point_480x640", "Oflow_sor_llin4_2d solver 1 (red-black point SOR)", "llin4", 480, 640, 64, 1, 4, 1.9, 60.0),
     # the reference's own line order (one CTA per problem, three problems per SM): latency-bound by construction, quoted
     # for what it costs to get the reference's iterates
@@ -544,6 +560,153 @@ def sweep_legs(ctx, dev, stream, dist, world, rank, steps=5):
 
 
 # ---------------------------------------------------------------------------------------------
+# band leg of the default line (BASELINE configs[4], second half): one N x N image in column bands, strong scaling.
+# Halo exchange through libpdegpu's own pdegpu_band_* (peer stores + device-side flags over NVLink; NCCL only carries the
+# 64-byte IPC handles once). With more than one rank the band path first proves itself bit-exact against a single-GPU
+# run of a small image (every rank relaxes the whole small image as well and compares its own columns).
+# ---------------------------------------------------------------------------------------------
+def band_fields(torch, dev, plan, nrows, seed):
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    shape = (plan.local_cols, nrows)
+    r = lambda lo, span: lo + span * torch.rand(shape, device=dev, generator=g)
+    f = {"U": r(-1, 2), "V": r(-1, 2), "dU": torch.zeros(shape, device=dev), "dV": torch.zeros(shape, device=dev)}
+    ix, iy, it = r(-0.5, 1), r(-0.5, 1), r(-0.5, 1)
+    gd = torch.clamp(1.0 / (0.042 * torch.sqrt(it * it + 1e-5)), max=50.0)
+    f.update({"M": gd * ix * iy, "Cu": gd * it * ix, "Cv": gd * it * iy, "Du": gd * ix * ix, "Dv": gd * iy * iy})
+    for k in ("wW", "wN", "wE", "wS"):
+        f[k] = r(0.2, 3.0)
+    torch.cuda.synchronize()                      # generated on torch's stream, relaxed on the library's
+    return f
+
+
+def band_selfcheck(ctx, dev, dist, world, rank, T):
+    """small image: the same full-image fields on every rank (same seed), bands against the whole image, bitwise"""
+    import torch
+    from pdegpu import bands, lib
+    n, iters = 1024, 2 * T + 1
+    whole = bands.BandPlan(n, n, 0, 1, sweeps_per_exchange=T)
+    full = band_fields(torch, dev, whole, n, 99)
+    plan = bands.BandPlan(n, n, rank, world, sweeps_per_exchange=T)
+    part = {k: v[plan.a0:plan.a1].clone() for k, v in full.items()}
+    torch.cuda.synchronize()
+    b = bands.GpuBand(ctx, plan, lib.FLOW_LLIN4, part, transport="p2p")
+    b.connect_p2p()
+    b.relax(iters, 1.0)
+    one = bands.GpuBand(ctx, whole, lib.FLOW_LLIN4, full, transport="p2p")
+    one.relax(iters, 1.0)
+    ctx.sync()
+    ok = bool(torch.equal(part["dU"][plan.own], full["dU"][plan.j0:plan.j1]) and torch.equal(part["dV"][plan.own], full["dV"][plan.j0:plan.j1]))
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    b.xchg.close()
+    return int(t.item()) == 0
+
+
+def band_leg(args, ctx, dev, stream, dist, world, rank, steps=5):
+    import torch
+    from pdegpu import bands, lib
+    N, T, iters = args.band_n, args.band_T, args.band_iters
+    bitwise = band_selfcheck(ctx, dev, dist, world, rank, T) if world > 1 else None
+    plan = bands.BandPlan(N, N, rank, world, sweeps_per_exchange=T)
+    f = band_fields(torch, dev, plan, N, 4242 + rank)
+    band = bands.GpuBand(ctx, plan, lib.FLOW_LLIN4, f, transport="p2p")
+    if world > 1:
+        band.connect_p2p()
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(3):
+        band.relax(iters, 1.0)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    sent = 0
+    for _ in range(steps):
+        sent += band.relax(iters, 1.0)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert torch.isfinite(f["dU"]).all()
+    peak, _ = measured_peaks()
+    value = N * N * iters * steps / 1e6 / (ms / 1e3)
+    out = {"metric": "Mpix*iter/s relax sweep (Oflow_sor_llin4_2d, red-black point SOR, one image in column bands)",
+           "what": f"configs[4]: one {N}x{N} image, llin4 flow system, solver 1, {iters} sweeps per step, column bands over {world} GPU(s), "
+                   f"halo of {plan.H} columns every {plan.T} sweep(s)",
+           "value": value, "unit": UNIT, "scaling": "strong", "ms_per_step": ms / steps,
+           "exchange": "pdegpu_band_exchange: peer stores + device-side flags over NVLink (csrc/band.cu), no host synchronisation per step",
+           "halo_bytes_sent_per_step_rank0": int(sent // max(1, steps)),
+           "whole_call_frac_of_peak_per_gpu": value * 1e6 * 60.0 / 1e9 / peak / world,
+           "bitwise_equal_to_single_gpu": bitwise}
+    if band.xchg:
+        band.xchg.close()
+    del f, band
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# batch leg of configs[4]: 512 synthetic 1080p pairs through the FMG driver, split over the GPUs (strong scaling)
+# ---------------------------------------------------------------------------------------------
+def batch512_leg(args, ctx, dev, stream, dist, world, rank):
+    import torch
+    from pdegpu import lib, synth
+    NR, NC, C = 1080, 1920, 1
+    total = args.batch512
+    mine = total // world + (1 if rank < total % world else 0)
+    L = lib.dll()
+    p = lib.FlowFmgParams()
+    L.pdegpu_flow_fmg_default_params(ctypes.byref(p))
+    pair = synth.image_pair(300 + 7 * rank, NR, NC, nframes=C, scale=255.0, max_flow=0.8)
+    chunk = 32                                      # pairs per call (one lane each): bounds the workspace
+    d0 = torch.from_numpy(np.stack([pair[0].reshape(-1, order="F")] * chunk)).to(dev)
+    d1 = torch.from_numpy(np.stack([pair[1].reshape(-1, order="F")] * chunk)).to(dev)
+    U = torch.empty(chunk, NR * NC, device=dev); V = torch.empty(chunk, NR * NC, device=dev)
+    ctx.set_sweep_order(lib.ORDER_FAST)
+
+    def run(npairs):
+        done = 0
+        while done < npairs:
+            k = min(chunk, npairs - done)
+            ctx._chk(L.pdegpu_dev_flow_fmg_2d(ctx.h, U.data_ptr(), V.data_ptr(), d0.data_ptr(), d1.data_ptr(), NR, NC, C, k, ctypes.byref(p)))
+            done += k
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(3):
+        run(min(chunk, mine))                       # direct run, capture, first replay
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    run(mine)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    assert torch.isfinite(U).all()
+    del d0, d1, U, V
+    torch.cuda.empty_cache()
+    return {"metric": "1920x1080 flows/s, batch of 512 pairs split over the GPUs (FlowEminNDFASFMG_elin_2D_v10 defaults)",
+            "what": f"configs[4]: {total} synthetic 1080p pairs, {mine} on rank 0, {chunk} per call side by side on lanes; no data-path collective",
+            "order": "fast (zebra lines)", "value": total / (ms / 1e3), "unit": "flows/s", "scaling": "strong", "s_per_batch": ms / 1e3}
+
+
+# ---------------------------------------------------------------------------------------------
 # band workload: one very large image, column bands, halo exchange per T sweeps (strong scaling)
 # ---------------------------------------------------------------------------------------------
 def run_band(args):
@@ -572,7 +735,9 @@ def run_band(args):
     for k in ("wW", "wN", "wE", "wS"):
         f[k] = r(0.2, 3.0)
     ctx = lib.Context(local)
-    band = bands.GpuBand(ctx, plan, lib.FLOW_LLIN4, f)
+    band = bands.GpuBand(ctx, plan, lib.FLOW_LLIN4, f, transport=args.band_transport)
+    if args.band_transport == "p2p" and world > 1:
+        band.connect_p2p()
     stream = band.stream
     omega = 1.0
 
@@ -624,7 +789,7 @@ def run_band(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"configs[4]: one {N}x{N} image, llin4 flow system, solver 1 (red-black), {args.band_iters} sweeps per step, "
-                                   f"column bands over {world} GPU(s), halo of {plan.H} columns exchanged every {plan.T} sweep(s) (NCCL send/recv)",
+                                   f"column bands over {world} GPU(s), halo of {plan.H} columns exchanged every {plan.T} sweep(s) ({args.band_transport})",
                        "l2": f"inputs larger than L2: {13 * plan.local_cols * N * 4 / 1e9:.1f} GB of fields per GPU",
                        "parallelism": f"band decomposition x{world}, neighbour halo exchange"},
             "halo_bytes_sent_per_step_rank0": sent // max(1, args.steps),
@@ -755,6 +920,8 @@ def run_ours(args):
         flows["reference_order"] = flows_leg(ctx, dev, stream, dist, world, rank, args.flow_ref_batch, reps=3, order=_lib.ORDER_REFERENCE, cpu=False)
     fmg = fmg_leg(ctx, dev, stream, dist, world, rank, args.fmg_pairs) if args.fmg_pairs > 0 else None
     sweeps = sweep_legs(ctx, dev, stream, dist, world, rank) if args.sweep_legs else None
+    band = band_leg(args, ctx, dev, stream, dist, world, rank) if args.band_leg else None
+    batch512 = batch512_leg(args, ctx, dev, stream, dist, world, rank) if args.batch512 > 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -792,6 +959,8 @@ def run_ours(args):
             "flows": flows,
             "fmg": fmg,
             "sweeps": sweeps,
+            "band": band,
+            "batch512_1080p": batch512,
             "kernels": prof,
             "clocks": clocks,
         }

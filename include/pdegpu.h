@@ -472,6 +472,33 @@ void pdegpu_tvdenoise8_default_params(pdegpu_tvdenoise8_params *p);
 int pdegpu_dev_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes, const pdegpu_tvdenoise8_params *params);
 int pdegpu_tvdenoise8(pdegpu_ctx *ctx, float *Iout, const float *Iin, int nrows, int ncols, int nframes, const pdegpu_tvdenoise8_params *params);
 
+/* ------------------------------------------------------------------------------------------
+ * One very large image on several GPUs: column bands with halo exchange (BASELINE configs[4]).
+ * The caller cuts the image along the slow axis (Matlab column index j) into contiguous bands with EVEN first columns,
+ * one per GPU, keeps every field of a band with H = 2T halo columns per inner side, and alternates
+ *     pdegpu_band_exchange(...);  pdegpu_dev_relax(ctx, &local_system, T, omega, 1);
+ * A red-black sweep spoils two columns from each cut, so after T sweeps exactly the halo is stale and the owned
+ * columns equal the single-GPU result bit for bit (pinned in tests/test_bands.py, tests/test_gpu_bands.py).
+ * The exchange is two kernels on the context's stream -- peer stores into the neighbour's mailbox over NVLink, step
+ * flags with system-scope release / acquire -- and no host synchronisation, NCCL call or event per step (csrc/band.cu).
+ * Neighbours are reached through CUDA IPC handles (one process per GPU: export, pass the 64 bytes to the neighbours by
+ * any means, connect) or directly (several contexts in one process: connect_local; peer access is enabled on demand).
+ * A process that drives SEVERAL bands must enqueue the exchange of step s for all of them before it does anything that
+ * may synchronise with the host on one of them (the first pdegpu_dev_relax of a context allocates its scratch and
+ * synchronises): exchange all, then relax all. With one process per GPU there is no such constraint.
+ * Only solver 1 splits this way: lines of the line solver along j cross the cuts.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct pdegpu_band pdegpu_band;
+int  pdegpu_band_create(pdegpu_ctx *ctx, int nrows, int halo_cols, int nunknowns, int has_left, int has_right, pdegpu_band **band);
+int  pdegpu_band_export(pdegpu_band *band, void *handle64);                                   /* cudaIpcMemHandle_t, 64 bytes */
+int  pdegpu_band_connect(pdegpu_band *band, const void *left_handle64, const void *right_handle64);   /* NULL where there is no neighbour */
+int  pdegpu_band_connect_local(pdegpu_band *band, pdegpu_band *left, pdegpu_band *right);
+/* unknowns[q]: the band's local array of unknown q (column-major, nrows rows, halo columns included, 16-byte aligned);
+ * [own0, own1): the owned columns in local indices. Asynchronous on the context's stream. */
+int  pdegpu_band_exchange(pdegpu_band *band, float *const unknowns[], int own0, int own1);
+unsigned long long pdegpu_band_bytes_sent(const pdegpu_band *band);
+void pdegpu_band_free(pdegpu_band *band);
+
 #ifdef __cplusplus
 }
 #endif

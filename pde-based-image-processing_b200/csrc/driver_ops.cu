@@ -21,6 +21,7 @@
 // documented behaviour: parity unpinned, checked against oracle/matlab_steps.py.
 // All kernels are streaming, HBM-bound, one thread per output pixel (fast axis = Matlab row index).
 #include "pdegpu_internal.cuh"
+#include "driver_formulas.cuh"
 
 namespace {
 
@@ -44,24 +45,9 @@ op_diff_weights_kernel(float *__restrict__ wW, float *__restrict__ wN, float *__
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= nr) return;
     const long long base = (long long)blockIdx.z * stride;
-    U += base; V += base;
-    auto at = [&](const float *F, int ii, int jj) -> double { return (double)F[(long long)jj * nr + ii]; };
-    // vertical / horizontal central differences [0.25 0 -0.25] (correlation, replicate border) at (ii, jj)
-    auto ver = [&](const float *F, int ii, int jj) -> double { return 0.25 * at(F, clampi(ii - 1, 0, nr - 1), jj) + (-0.25) * at(F, clampi(ii + 1, 0, nr - 1), jj); };
-    auto hor = [&](const float *F, int ii, int jj) -> double { return 0.25 * at(F, ii, clampi(jj - 1, 0, nc - 1)) + (-0.25) * at(F, ii, clampi(jj + 1, 0, nc - 1)); };
-    const int jw = wrapi(j - 1, nc), je = wrapi(j + 1, nc), in_ = wrapi(i - 1, nr), is = wrapi(i + 1, nr);
-    const double u = at(U, i, j), v = at(V, i, j);
-    const double uver = ver(U, i, j), vver = ver(V, i, j), uhor = hor(U, i, j), vhor = hor(V, i, j);
-    auto sq = [](double x) { return x * x; };
-    const double sW = sq(at(U, i, jw) - u) + sq(uver + ver(U, i, jw)) + sq(at(V, i, jw) - v) + sq(vver + ver(V, i, jw));
-    const double sE = sq(at(U, i, je) - u) + sq(uver + ver(U, i, je)) + sq(at(V, i, je) - v) + sq(vver + ver(V, i, je));
-    const double sN = sq(at(U, in_, j) - u) + sq(uhor + hor(U, in_, j)) + sq(at(V, in_, j) - v) + sq(vhor + hor(V, in_, j));
-    const double sS = sq(at(U, is, j) - u) + sq(uhor + hor(U, is, j)) + sq(at(V, is, j) - v) + sq(vhor + hor(V, is, j));
+    const OpdiffSrc src = {U + base, V + base, nullptr, nullptr};
     const long long p = base + (long long)j * nr + i;
-    wW[p] = (float)(1.0 / sqrt(sW + 0.00001));
-    wE[p] = (float)(1.0 / sqrt(sE + 0.00001));
-    wN[p] = (float)(1.0 / sqrt(sN + 0.00001));
-    wS[p] = (float)(1.0 / sqrt(sS + 0.00001));
+    opdiff_at(src, i, j, nr, nc, wW[p], wN[p], wS[p], wE[p]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -71,18 +57,6 @@ __device__ __forceinline__ float mulf(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float addf(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float subf(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float sqf(float a) { return __fmul_rn(a, a); }
-__device__ __forceinline__ float nansum_add(float acc, float t) { return is_nan(t) ? acc : __fadd_rn(acc, t); }
-
-struct LlinTermsArgs {
-    const float *d1[3];       // I1dt, I1dx, I1dy                       (c1 channels)
-    const float *d2[5];       // I2dt, I2dx, I2dy | I2dxt, I2dyt, I2dxx, I2dyy, I2dxy   (c2 channels)
-    const float *dU, *dV;
-    float *out[5];            // M, Cu, Cv, Du, Dv
-    int c1, c2, gradmag;
-    float b1, b2, alpha;
-    long long npix;           // pixels per channel
-    long long stride1, stride2, stride;   // batch strides of the d1 stacks, the d2 stacks, and of dU/dV/outputs
-};
 
 __global__ void __launch_bounds__(256)
 llin_terms_kernel(const LlinTermsArgs a)
@@ -90,40 +64,8 @@ llin_terms_kernel(const LlinTermsArgs a)
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.npix) return;
     const long long b = blockIdx.y;
-    const float du = a.dU[b * a.stride + t], dv = a.dV[b * a.stride + t];
-    float M = 0.f, Cu = 0.f, Cv = 0.f, Du = 0.f, Dv = 0.f;
-    for (int c = 0; c < a.c1; c++) {
-        const long long p = b * a.stride1 + (long long)c * a.npix + t;
-        const float It = a.d1[0][p], Ix = a.d1[1][p], Iy = a.d1[2][p];
-        const float r = subf(subf(It, mulf(Ix, du)), mulf(Iy, dv));
-        const float g = __fdiv_rn(a.b1, mulf(a.alpha, __fsqrt_rn(addf(sqf(r), 0.00001f))));
-        M = nansum_add(M, mulf(mulf(Iy, Ix), g));
-        Cu = nansum_add(Cu, mulf(mulf(It, Ix), g));
-        Cv = nansum_add(Cv, mulf(mulf(It, Iy), g));
-        Du = nansum_add(Du, mulf(mulf(Ix, Ix), g));
-        Dv = nansum_add(Dv, mulf(mulf(Iy, Iy), g));
-    }
-    // the driver sums cat(3, X1.*gD1, X2.*gD2): all first-term channels, then all second-term channels
-    for (int c = 0; c < a.c2; c++) {
-        const long long p = b * a.stride2 + (long long)c * a.npix + t;
-        float m2, cu2, cv2, du2, dv2, op;
-        if (!a.gradmag) {
-            const float It = a.d2[0][p], Ix = a.d2[1][p], Iy = a.d2[2][p];
-            op = sqf(subf(subf(It, mulf(Ix, du)), mulf(Iy, dv)));
-            m2 = mulf(Iy, Ix); cu2 = mulf(It, Ix); cv2 = mulf(It, Iy); du2 = mulf(Ix, Ix); dv2 = mulf(Iy, Iy);
-        } else {
-            const float xt = a.d2[0][p], yt = a.d2[1][p], xx = a.d2[2][p], yy = a.d2[3][p], xy = a.d2[4][p];
-            op = addf(sqf(subf(subf(xt, mulf(xx, du)), mulf(xy, dv))), sqf(subf(subf(yt, mulf(xy, du)), mulf(yy, dv))));
-            m2 = mulf(xy, addf(xx, yy));
-            cu2 = addf(mulf(xt, xx), mulf(yt, xy));
-            cv2 = addf(mulf(xt, xy), mulf(yt, yy));
-            du2 = addf(mulf(xx, xx), mulf(xy, xy));
-            dv2 = addf(mulf(xy, xy), mulf(yy, yy));
-        }
-        const float g = __fdiv_rn(a.b2, mulf(a.alpha, __fsqrt_rn(addf(op, 0.00001f))));
-        M = nansum_add(M, mulf(m2, g)); Cu = nansum_add(Cu, mulf(cu2, g)); Cv = nansum_add(Cv, mulf(cv2, g));
-        Du = nansum_add(Du, mulf(du2, g)); Dv = nansum_add(Dv, mulf(dv2, g));
-    }
+    float M, Cu, Cv, Du, Dv;
+    llin_terms_at(a, b, t, a.dU[b * a.stride + t], a.dV[b * a.stride + t], M, Cu, Cv, Du, Dv);
     const long long o = b * a.stride + t;
     a.out[0][o] = M; a.out[1][o] = Cu; a.out[2][o] = Cv; a.out[3][o] = Du; a.out[4][o] = Dv;
 }

@@ -5,6 +5,7 @@
 // GS_ALR_SOR_llin4_2d (disparitySolvers.c:154) and GS_ALR_SOR_4_2d (pdeSolvers.c:277).
 #include "sweeps_tline_impl.cuh"
 #include "sweeps_lex_impl.cuh"
+#include "driver_formulas.cuh"
 #include <cstdlib>
 
 namespace {
@@ -22,6 +23,9 @@ struct PrepParams {
     int S0, ns0, S1, ns1;                    // segments per line and their length: column pass (cuts along i), row pass (along j)
     long long ibs;                           // floats between problems of the inputs
     float *pn, *pt, *tn;                     // packed coefficient lines: column pass / row pass; packed T lines (column pass)
+    // FUSED preparation (late-linearisation flow driver, north_star subsystem 3): the diffusion weights (OPdiffWeights of
+    // x0 + x) and the robust data terms M, C, D are computed here, per pixel, instead of being read: w, m, c, d unused
+    LlinTermsArgs terms;
 };
 
 // C' = C + D x0 + M y0. Where the reference's row would produce NaN (a number for C next to a NaN D or M) C' stays a
@@ -34,7 +38,7 @@ __device__ __forceinline__ float tl_cprime(float C, float D, float M, float x0, 
     return v;
 }
 
-template <int FAM>
+template <int FAM, bool FUSED = false>
 __global__ void __launch_bounds__(256)
 tline_prep_kernel(const PrepParams p)
 {
@@ -61,12 +65,26 @@ tline_prep_kernel(const PrepParams p)
         const int jc = min(j0 + ty + 8 * r, p.ncols - 1);
         const long long src = (long long)b * p.ibs + (long long)jc * p.nrows + ic;
 #pragma unroll
-        for (int k = 0; k < NN; k++) vw[r][k] = p.w[wsrc[k] % NN == wsrc[k] ? wsrc[k] : 0][src];
-        vm[r] = NUNK == 2 ? p.m[src] : 0.f;
-#pragma unroll
         for (int q = 0; q < NUNK; q++) {
-            vc[r][q] = p.c[q][src]; vd[r][q] = p.d[q][src]; vx[r][q] = p.x[q][src];
+            vx[r][q] = p.x[q][src];
             vx0[r][q] = F::LATE ? p.x0[q][src] : 0.f;
+        }
+        if (FUSED) {
+            // FlowEminND_llin_2D_v10.m:321 (OPdiffWeights(U+dU, V+dV)) and :289-327 (robust weights, channel sums)
+            const long long pb = (long long)b * p.ibs;
+            const OpdiffSrc os = {p.x0[0] + pb, p.x0[NUNK - 1] + pb, p.x[0] + pb, p.x[NUNK - 1] + pb};
+            float wW, wN, wS, wE;
+            opdiff_at(os, ic, jc, p.nrows, p.ncols, wW, wN, wS, wE);
+            vw[r][0] = wN; vw[r][1] = wS; vw[r][2] = wW; vw[r][3] = wE;       // wsrc order: N S W E
+            float M, Cu, Cv, Du, Dv;
+            llin_terms_at(p.terms, b, (long long)jc * p.nrows + ic, vx[r][0], vx[r][NUNK - 1], M, Cu, Cv, Du, Dv);
+            vm[r] = M; vc[r][0] = Cu; vc[r][NUNK - 1] = Cv; vd[r][0] = Du; vd[r][NUNK - 1] = Dv;
+        } else {
+#pragma unroll
+            for (int k = 0; k < NN; k++) vw[r][k] = p.w[wsrc[k] % NN == wsrc[k] ? wsrc[k] : 0][src];
+            vm[r] = NUNK == 2 ? p.m[src] : 0.f;
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) { vc[r][q] = p.c[q][src]; vd[r][q] = p.d[q][src]; }
         }
     }
 #pragma unroll

@@ -97,10 +97,15 @@ class GpuBand:
     fields: dict name -> torch tensor [local_cols, nrows] on this rank's GPU (halo columns included);
     unknown names first in `unknowns`."""
 
-    def __init__(self, ctx, plan: BandPlan, family: int, fields: Dict[str, "object"], group=None):
+    def __init__(self, ctx, plan: BandPlan, family: int, fields: Dict[str, "object"], group=None, transport: str = "nccl"):
+        """transport "nccl": halo columns through torch.distributed send / recv (exchange_halos); "p2p": libpdegpu's own
+        exchange (pdegpu_band_*: peer stores + flags over NVLink, no host synchronisation per step), set up with
+        connect_p2p() (one process per GPU) or connect_local() (several bands in one process)."""
         import torch
         from . import lib
         self.ctx, self.plan, self.family, self.f, self.group = ctx, plan, family, fields, group
+        self.transport = transport
+        self.xchg = None
         self.stream = torch.cuda.ExternalStream(ctx.stream, device=next(iter(fields.values())).device)
         nr, lc = plan.nrows, plan.local_cols
         p = lambda k: fields[k].data_ptr()
@@ -118,8 +123,44 @@ class GpuBand:
         else:
             raise ValueError("band split is built for the flow and PDE4 families")
 
-    def relax(self, iters: int, omega: float) -> int:
-        """`iters` red-black sweeps with halo exchanges; NCCL and libpdegpu are ordered through the context's stream."""
+    def _make_exchange(self):
+        from . import lib
+        p = self.plan
+        if self.xchg is None:
+            self.xchg = lib.BandExchange(self.ctx, p.nrows, p.H, len(self.unknowns), p.left is not None, p.right is not None)
+        return self.xchg
+
+    def connect_p2p(self):
+        """one process per GPU: all-gather the mailboxes' IPC handles over torch.distributed, open the neighbours'"""
         import torch
+        import torch.distributed as dist
+        x = self._make_exchange()
+        mine = torch.frombuffer(bytearray(x.export()), dtype=torch.uint8).to(self.unknowns[0].device)
+        everyone = [torch.empty_like(mine) for _ in range(self.plan.world)]
+        dist.all_gather(everyone, mine, group=self.group)
+        h = lambda r: bytes(everyone[r].cpu().numpy().tobytes()) if r is not None else None
+        x.connect(h(self.plan.left), h(self.plan.right))
+        dist.barrier(group=self.group)
+
+    def connect_local(self, left: "GpuBand | None", right: "GpuBand | None"):
+        self._make_exchange().connect_local(left._make_exchange() if left is not None else None,
+                                            right._make_exchange() if right is not None else None)
+
+    def exchange_p2p(self):
+        p = self.plan
+        self.xchg.exchange([u.data_ptr() for u in self.unknowns], p.own.start, p.own.stop)
+
+    def relax(self, iters: int, omega: float) -> int:
+        """`iters` red-black sweeps with halo exchanges, everything ordered through the context's stream."""
+        import torch
+        if self.transport == "p2p":
+            done, before = 0, self.xchg.bytes_sent if self.xchg else 0
+            while done < iters:
+                n = min(self.plan.T, iters - done)
+                if self.plan.world > 1:
+                    self.exchange_p2p()
+                self.ctx.relax(self.sys, n, omega, 1)
+                done += n
+            return (self.xchg.bytes_sent - before) if self.xchg else 0
         with torch.cuda.stream(self.stream):
             return relax_bands(self.plan, self.unknowns, lambda n: self.ctx.relax(self.sys, n, omega, 1), iters, self.group)

@@ -128,6 +128,20 @@ def dll() -> ctypes.CDLL:
         L.pdegpu_get_sweep_order.argtypes = [c_void_p]
         L.pdegpu_dev_relax.restype = c_int
         L.pdegpu_dev_relax.argtypes = [c_void_p, POINTER(System), c_int, c_float, c_int]
+        L.pdegpu_band_create.restype = c_int
+        L.pdegpu_band_create.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p)]
+        L.pdegpu_band_export.restype = c_int
+        L.pdegpu_band_export.argtypes = [c_void_p, c_void_p]
+        L.pdegpu_band_connect.restype = c_int
+        L.pdegpu_band_connect.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.pdegpu_band_connect_local.restype = c_int
+        L.pdegpu_band_connect_local.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.pdegpu_band_exchange.restype = c_int
+        L.pdegpu_band_exchange.argtypes = [c_void_p, POINTER(c_void_p), c_int, c_int]
+        L.pdegpu_band_bytes_sent.restype = c_ulonglong
+        L.pdegpu_band_bytes_sent.argtypes = [c_void_p]
+        L.pdegpu_band_free.restype = None
+        L.pdegpu_band_free.argtypes = [c_void_p]
         L.pdegpu_dev_residual.restype = c_int
         L.pdegpu_dev_residual.argtypes = [c_void_p, POINTER(System), c_int, c_void_p, c_void_p]
         L.pdegpu_dev_lhs.restype = c_int
@@ -378,3 +392,40 @@ def make_system(family: int, nrows: int, ncols: int, batch: int = 1, batch_strid
     for k, p in enumerate(w):
         s.w[k] = p
     return s
+
+
+class BandExchange:
+    """pdegpu_band_* (include/pdegpu.h): the halo exchange of one band over peer memory. `export()` gives the 64-byte
+    CUDA IPC handle of this band's mailbox; `connect(left, right)` takes the neighbours' handles (bytes; one process per
+    GPU) and `connect_local(left, right)` other BandExchange objects of the same process."""
+
+    def __init__(self, ctx: "Context", nrows: int, halo_cols: int, nunknowns: int, has_left: bool, has_right: bool):
+        self.ctx = ctx
+        self.h = c_void_p()
+        ctx._chk(dll().pdegpu_band_create(ctx.h, nrows, halo_cols, nunknowns, int(has_left), int(has_right), ctypes.byref(self.h)))
+
+    def export(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        self.ctx._chk(dll().pdegpu_band_export(self.h, buf))
+        return buf.raw
+
+    def connect(self, left: "bytes | None", right: "bytes | None"):
+        l = ctypes.create_string_buffer(left, 64) if left else None
+        r = ctypes.create_string_buffer(right, 64) if right else None
+        self.ctx._chk(dll().pdegpu_band_connect(self.h, l, r))
+
+    def connect_local(self, left: "BandExchange | None", right: "BandExchange | None"):
+        self.ctx._chk(dll().pdegpu_band_connect_local(self.h, left.h if left else None, right.h if right else None))
+
+    def exchange(self, unknown_ptrs, own0: int, own1: int):
+        arr = (c_void_p * len(unknown_ptrs))(*unknown_ptrs)
+        self.ctx._chk(dll().pdegpu_band_exchange(self.h, arr, own0, own1))
+
+    @property
+    def bytes_sent(self) -> int:
+        return int(dll().pdegpu_band_bytes_sent(self.h))
+
+    def close(self):
+        if self.h:
+            dll().pdegpu_band_free(self.h)
+            self.h = c_void_p()
