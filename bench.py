@@ -493,6 +493,7 @@ SWEEP_LEGS = [
     ("sweep_tv_4096x2160", "PDEsolver4 (TVdenoise4.m:85-90 at the configs[3] image size)", "pde4", 2160, 4096, 4, 2, 4, 1.75, 32.0),
     ("tv8_4096x2160", "PDEsolver8 (TVdenoise8.m:87-100 at the configs[3] image size; ONE line iteration per call, SURVEY Q4)", "pde8", 2160, 4096, 4, 2, 1, 1.75, 48.0),
     ("point_480x640", "Oflow_sor_llin4_2d solver 1 (red-black point SOR)", "llin4", 480, 640, 64, 1, 4, 1.9, 60.0),
+    ("point_window_480x640", "Oflow_sor_llin4_2d solver 1, temporally blocked: TWO sweeps per pass over HBM (rb_window_kernel, 148 problems = 5 strips per SM)", "llin4", 480, 640, 148, 1, 4, 1.9, 60.0),
     # the reference's own line order (one CTA per problem, three problems per SM): latency-bound by construction, quoted
     # for what it costs to get the reference's iterates
     ("reference_order_480x640", "Oflow_sor_llin4_2d solver 2 in the reference's lexicographic line order (PDEGPU_ORDER_REFERENCE)", "llin4", 480, 640, 444, 2, 4, 1.9, 60.0),

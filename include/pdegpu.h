@@ -310,6 +310,14 @@ typedef struct pdegpu_llin_terms {
     long long batch_stride1, batch_stride2, batch_stride;   /* of the d1 stacks, the d2 stacks, dU/dV/out */
 } pdegpu_llin_terms;
 int pdegpu_dev_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t);
+/* One inner solve of the late-linearisation flow driver, FlowEminND_llin_2D_v10.m:278-348, in ONE call:
+ * OPdiffWeights(U+dU, V+dV) (:321), the robust data weights and channel sums (:289-327, `t`; t->dU, t->dV and t->out are
+ * ignored) and Oflow_sor_llin4_2d (:332-348) relaxing dU, dV in place. With solver 2 on the packed-line kernels the
+ * weights and terms are computed inside the kernel that prepares the lines and are never written as arrays (north_star
+ * subsystem 3: weight stencils fused into the sweep's producer); otherwise the steps run one after the other through
+ * `work` (11 * batch * batch_stride floats of device memory). Results are identical either way. */
+int pdegpu_dev_llin_solve(pdegpu_ctx *ctx, const pdegpu_llin_terms *t, const float *U, const float *V, float *dU, float *dV,
+                          float *work, int iter, float omega, int solver);
 
 /* gd and gd-weighted terms of the FMG early-linearisation smoother:
  * summed != 0: FlowEminNDFASFMG_elin_2D_v10.m:375-396 (gd = 1/(channels*alpha*sqrt(.)), terms summed over

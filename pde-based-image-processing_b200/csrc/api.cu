@@ -535,6 +535,43 @@ extern "C" int pdegpu_dev_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t
     return op_llin_terms(ctx, t);
 }
 
+// The inner solve of the late-linearisation flow driver, FlowEminND_llin_2D_v10.m:278-348, as ONE call: diffusion
+// weights of (U+dU, V+dV), robust data weights and channel sums, Oflow_sor_llin4_2d. Where the line kernels run from
+// packed lines (generation 3 and the reference order) weights and terms are computed inside their preparation kernel
+// and never exist as arrays (north_star subsystem 3); elsewhere the three steps run one after the other through `work`.
+extern "C" int pdegpu_dev_llin_solve(pdegpu_ctx *ctx, const pdegpu_llin_terms *t, const float *U, const float *V, float *dU, float *dV,
+                                     float *work, int iter, float omega, int solver)
+{
+    PDEGPU_ENTER(ctx);
+    if (!t || !U || !V || !dU || !dV || !work || t->nrows < 3 || t->ncols < 3 || t->batch < 1 || t->channels1 < 1 || t->channels2 < 0)
+        return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_solve: bad argument");
+    for (int k = 0; k < 3; k++) if (!t->d1[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_solve: d1[%d] is NULL", k);
+    for (int k = 0; k < (t->channels2 ? (t->gradmag ? 5 : 3) : 0); k++) if (!t->d2[k]) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_solve: d2[%d] is NULL", k);
+    if (solver != 1 && solver != 2) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_llin_solve: no such solver %d", solver);
+    const long long n = t->batch_stride, all = n * t->batch;
+    pdegpu_llin_terms tt = *t;
+    tt.dU = dU; tt.dV = dV;
+    pdegpu_system sys;
+    memset(&sys, 0, sizeof sys);
+    sys.family = PDEGPU_FLOW_LLIN4; sys.nrows = t->nrows; sys.ncols = t->ncols; sys.batch = t->batch; sys.batch_stride = n;
+    sys.x[0] = dU; sys.x[1] = dV; sys.x0[0] = U; sys.x0[1] = V;
+    if (solver == 2 && ctx->kernel_path == 1 && iter > 0) {
+        const int rc = relax_llin_fused(ctx, &sys, &tt, iter, omega, ctx->sweep_order == PDEGPU_ORDER_REFERENCE);
+        if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
+    }
+    float *Us = work, *Vs = work + all, *w[4], *T[5];
+    for (int k = 0; k < 4; k++) w[k] = work + (2 + k) * all;
+    for (int k = 0; k < 5; k++) { T[k] = work + (6 + k) * all; tt.out[k] = T[k]; }
+    int rc;
+    if ((rc = op_axpby(ctx, Us, 1.0f, U, 1.0f, dU, all))) return rc;
+    if ((rc = op_axpby(ctx, Vs, 1.0f, V, 1.0f, dV, all))) return rc;
+    if ((rc = op_opdiff(ctx, w[0], w[1], w[2], w[3], Us, Vs, t->nrows, t->ncols, t->batch, n))) return rc;       // [wW wN wS wE]
+    if ((rc = op_llin_terms(ctx, &tt))) return rc;
+    sys.m = T[0]; sys.c[0] = T[1]; sys.c[1] = T[2]; sys.d[0] = T[3]; sys.d[1] = T[4];
+    sys.w[W_W] = w[0]; sys.w[W_N] = w[1]; sys.w[W_S] = w[2]; sys.w[W_E] = w[3];
+    return pdegpu_dev_relax(ctx, &sys, iter, omega, solver);
+}
+
 extern "C" int pdegpu_dev_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t)
 {
     PDEGPU_ENTER(ctx);

@@ -119,9 +119,7 @@ int flow_llin_run(pdegpu_ctx *ctx, Bump &b, float *Uout, float *Vout, const floa
     float *D1[3], *D2[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < 3; k++) D1[k] = b.take(np0 * c1 * B);
     for (int k = 0; k < (c2 ? (gradmag ? 5 : 3) : 0); k++) D2[k] = b.take(np0 * c2 * B);
-    float *T[5], *w[4];
-    for (int k = 0; k < 5; k++) T[k] = b.take(np0 * B);
-    for (int k = 0; k < 4; k++) w[k] = b.take(np0 * B);       // wW, wN, wS, wE (OPdiffWeights' order)
+    float *lwork = b.take(np0 * B * 11);                      // pdegpu_dev_llin_solve's scratch (only its unfused path uses it)
     if (dry) return PDEGPU_OK;
 
     const float up = (float)(1.0 / P.scl_factor);
@@ -141,25 +139,16 @@ int flow_llin_run(pdegpu_ctx *ctx, Bump &b, float *Uout, float *Vout, const floa
             }
             RC(fill_zero(ctx, dU, n * B)); RC(fill_zero(ctx, dV, n * B));
             for (int sl = 0; sl < P.secondLoop; sl++) {
-                RC(op_axpby(ctx, Us, 1.0f, U, 1.0f, dU, n * B));
-                RC(op_axpby(ctx, Vs, 1.0f, V, 1.0f, dV, n * B));
-                RC(op_opdiff(ctx, w[0], w[1], w[2], w[3], Us, Vs, nr, nc, B, n));            // (:321)
+                // OPdiffWeights (:321), robust weights + channel sums (:289-327), Oflow_sor_llin4_2d (:332-348): one call,
+                // fused into the line kernels' preparation where they run from packed lines (pdegpu_dev_llin_solve)
                 pdegpu_llin_terms t;
                 memset(&t, 0, sizeof t);
                 t.nrows = nr; t.ncols = nc; t.batch = B; t.channels1 = c1; t.channels2 = c2; t.gradmag = gradmag;
                 t.b1 = (float)P.b1; t.b2 = (float)P.b2; t.alpha = (float)P.alpha;
                 for (int k = 0; k < 3; k++) t.d1[k] = D1[k];
-                for (int k = 0; k < 5; k++) { t.d2[k] = D2[k]; t.out[k] = T[k]; }
-                t.dU = dU; t.dV = dV;
+                for (int k = 0; k < 5; k++) t.d2[k] = D2[k];
                 t.batch_stride1 = n * c1; t.batch_stride2 = n * (c2 ? c2 : 1); t.batch_stride = n;
-                RC(op_llin_terms(ctx, &t));                                                  // (:289-327)
-                pdegpu_system sys;
-                memset(&sys, 0, sizeof sys);
-                sys.family = PDEGPU_FLOW_LLIN4; sys.nrows = nr; sys.ncols = nc; sys.batch = B; sys.batch_stride = n;
-                sys.x[0] = dU; sys.x[1] = dV; sys.x0[0] = U; sys.x0[1] = V;
-                sys.m = T[0]; sys.c[0] = T[1]; sys.c[1] = T[2]; sys.d[0] = T[3]; sys.d[1] = T[4];
-                sys.w[W_W] = w[0]; sys.w[W_N] = w[1]; sys.w[W_S] = w[2]; sys.w[W_E] = w[3];
-                RC(pdegpu_dev_relax(ctx, &sys, P.iter, (float)P.omega, P.solver));           // (:332-348)
+                RC(pdegpu_dev_llin_solve(ctx, &t, U, V, dU, dV, lwork, P.iter, (float)P.omega, P.solver));
             }
             // U = medfilt2(U + dU, [3 3], 'symmetric')  (:354-355)
             RC(op_axpby(ctx, Us, 1.0f, U, 1.0f, dU, n * B));

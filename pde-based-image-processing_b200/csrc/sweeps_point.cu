@@ -400,6 +400,11 @@ __global__ void border_fill_tile_kernel(float *x0, float *x1, int nr, int nc, lo
     for (int q = 0; q < NUNK; q++) x[q][base + (long long)j * nr + i] = x[q][base + (long long)jc * nr + ic];
 }
 
+}  // namespace
+// two sweeps per pass over HBM (sweeps_tpoint.cu)
+int relax_tpoint(pdegpu_ctx *ctx, const pdegpu_system *sys, float *const cur[2], float *const alt[2], int pairs, float omega, bool *result_in_alt);
+namespace {
+
 template <int FAM>
 int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
 {
@@ -427,6 +432,17 @@ int run_point_tiles(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
     const int per = 2 * sys->nrows + 2 * sys->ncols;
     dim3 bgrid((per + 127) / 128, sys->batch);
     float *cur[2] = {sys->x[0], sys->x[1]}, *nxt[2] = {alt[0], alt[1]};
+    // pairs of sweeps: the temporally blocked kernel (every field read once per TWO sweeps) where it wins (enough strips
+    // to fill the SMs three times: sweeps_tpoint.cu; PDEGPU_POINT_WINDOW=1 / 0 forces it on / off); a last odd sweep and
+    // everything else: one sweep per pass as before.
+    if (al && iter >= 2) {
+        bool in_alt = false;
+        rc = relax_tpoint(ctx, sys, cur, nxt, iter / 2, omega, &in_alt);
+        if (rc == PDEGPU_OK) {
+            if (in_alt) for (int q = 0; q < 2; q++) { float *t = cur[q]; cur[q] = nxt[q]; nxt[q] = t; }
+            iter &= 1;
+        } else if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
+    }
     for (int it = 0; it < iter; it++) {
         v.x[0] = cur[0]; v.x[1] = cur[1];
         PDEGPU_PROF(ctx, "rb_tile_kernel", sweep_bytes<FAM>() * (double)npix * sys->batch);

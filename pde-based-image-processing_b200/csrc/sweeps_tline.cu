@@ -249,8 +249,27 @@ static SegPlan seg_plan(int n)
     return s;
 }
 
+// launch of the preparation kernel, plain or fused (`terms` given: FLOW_LLIN4 only)
 template <int FAM>
-int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+int tline_prep_launch(pdegpu_ctx *ctx, const PrepParams &pp, dim3 grid, size_t smem, const LlinTermsArgs *terms)
+{
+    if (terms && FAM == PDEGPU_FLOW_LLIN4) {
+        PrepParams q = pp;
+        q.terms = *terms;
+        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
+        tline_prep_kernel<FAM, true><<<grid, 256, smem, ctx->stream>>>(q);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
+        tline_prep_kernel<FAM, false><<<grid, 256, smem, ctx->stream>>>(pp);
+    }
+    PDEGPU_LAUNCH_CHECK(ctx, "tline_prep_kernel");
+    return PDEGPU_OK;
+}
+
+template <int FAM>
+int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, const LlinTermsArgs *terms = nullptr)
 {
     using F = Fam<FAM>;
     constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, MODE = F::PDE ? 1 : 0;
@@ -290,14 +309,12 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
         pp.S0 = s0.S; pp.ns0 = s0.ns; pp.S1 = s1.S; pp.ns1 = s1.ns;
         pp.ibs = sys->batch_stride; pp.pn = PN; pp.pt = PT; pp.tn = TN;
         const size_t smem = (size_t)NC * 32 * 33 * sizeof(float);
-        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
         const int ci = nr > s0.S * pitch0 ? nr : s0.S * pitch0, cj = nc > s1.S * pitch1 ? nc : s1.S * pitch1;   // incl. the pads
         dim3 grid((ci + 31) / 32, (cj + 31) / 32, batch);
-        const double fields_in = NN + (NUNK == 2 ? 1 : 0) + NUNK * (F::LATE ? 4 : 3), fields_out = 2 * NC + NUNK;
-        PDEGPU_PROF(ctx, "tline_prep_kernel", 4.0 * (fields_in + fields_out) * nr * nc * batch);
-        tline_prep_kernel<FAM><<<grid, 256, smem, ctx->stream>>>(pp);
-        PDEGPU_LAUNCH_CHECK(ctx, "tline_prep_kernel");
+        const double fields_in = terms ? 4.0 + 3.0 * terms->c1 + (terms->gradmag ? 5.0 : 3.0) * terms->c2
+                                       : NN + (NUNK == 2 ? 1 : 0) + NUNK * (F::LATE ? 4 : 3), fields_out = 2 * NC + NUNK;
+        PDEGPU_PROF(ctx, terms ? "tline_prep_kernel<fused weights+terms>" : "tline_prep_kernel", 4.0 * (fields_in + fields_out) * nr * nc * batch);
+        if ((rc = tline_prep_launch<FAM>(ctx, pp, grid, smem, terms))) return rc;
     }
 
     TLParams p0, p1;
@@ -525,7 +542,7 @@ int lex_pass(pdegpu_ctx *ctx, LexParams &p, int batch, double bytes, const char 
 }
 
 template <int FAM>
-int lex_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+int lex_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, const LlinTermsArgs *terms = nullptr)
 {
     using F = Fam<FAM>;
     constexpr int NUNK = F::NUNK, NN = F::EIGHT ? 8 : 4, MODE = F::PDE ? 1 : 0;
@@ -558,12 +575,9 @@ int lex_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
         pp.S0 = 1; pp.ns0 = pitch0 > nr ? pitch0 : nr; pp.S1 = 1; pp.ns1 = pitch1 > nc ? pitch1 : nc;
         pp.ibs = sys->batch_stride; pp.pn = PN; pp.pt = PT; pp.tn = TN;
         const size_t smem = (size_t)NC * 32 * 33 * sizeof(float);
-        cudaError_t e = cudaFuncSetAttribute(tline_prep_kernel<FAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(tline_prep_kernel)");
         dim3 grid((pitch0 + 31) / 32, (pitch1 + 31) / 32, batch);
-        PDEGPU_PROF(ctx, "tline_prep_kernel", 0);
-        tline_prep_kernel<FAM><<<grid, 256, smem, ctx->stream>>>(pp);
-        PDEGPU_LAUNCH_CHECK(ctx, "tline_prep_kernel");
+        PDEGPU_PROF(ctx, terms ? "tline_prep_kernel<fused weights+terms>" : "tline_prep_kernel", 0);
+        if ((rc = tline_prep_launch<FAM>(ctx, pp, grid, smem, terms))) return rc;
     }
     LexParams p0, p1;
     memset(&p0, 0, sizeof(p0));
@@ -654,4 +668,35 @@ int relax_lexline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float ome
     case PDEGPU_PDE8:       return lex_run<PDEGPU_PDE8>(ctx, sys, iter, omega);
     default: return PDEGPU_ERR_UNSUPPORTED;
     }
+}
+
+// The late-linearisation flow driver's inner solve with the diffusion weights and the data terms computed INSIDE the
+// preparation of the packed lines (pdegpu_dev_llin_solve, api.cu). sys: family FLOW_LLIN4 with x, x0 set; w, m, c, d are
+// not read. PDEGPU_ERR_UNSUPPORTED: this call takes another path (small problems resident in shared memory, short
+// lines), the caller runs the three steps one after the other.
+int relax_llin_fused(pdegpu_ctx *ctx, const pdegpu_system *sys, const pdegpu_llin_terms *t, int iter, float omega, bool reference_order)
+{
+    if (iter <= 0) return PDEGPU_ERR_UNSUPPORTED;
+    // OFF unless PDEGPU_FUSE=1. Measured (B200, 16 pairs of 640x480, whole llin driver): the fused preparation takes
+    // 31.7 ms per batch against 21.8 ms for the four kernels it replaces (two axpby, op_diff_weights, llin_terms) plus the
+    // plain preparation: it holds 124 registers for 4 pixels per thread (16 warps per SM) and evaluates the double-
+    // precision weight stencil serially per pixel, where the stand-alone kernels run one pixel per thread at full
+    // occupancy and already stream at 3-5 TB/s. 512 launches fewer per batch, 6 % fewer flows/s.
+    static const int enabled = env_int("PDEGPU_FUSE", 0);
+    if (!enabled) return PDEGPU_ERR_UNSUPPORTED;
+    LlinTermsArgs a;
+    memset(&a, 0, sizeof a);
+    for (int k = 0; k < 3; k++) a.d1[k] = t->d1[k];
+    for (int k = 0; k < 5; k++) a.d2[k] = t->d2[k];
+    a.c1 = t->channels1; a.c2 = t->channels2; a.gradmag = t->gradmag;
+    a.b1 = t->b1; a.b2 = t->b2; a.alpha = t->alpha;
+    a.npix = (long long)t->nrows * t->ncols;
+    a.stride1 = t->batch_stride1; a.stride2 = t->batch_stride2; a.stride = t->batch_stride;
+    if (reference_order) return lex_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega, &a);
+    {   // the shared-memory resident kernel takes dense arrays: leave small problems to the unfused sequence
+        const int nr = sys->nrows, nc = sys->ncols, nmax = nr > nc ? nr : nc;
+        const size_t smem = (size_t)11 * (nr | 1) * nc * sizeof(float);
+        if (env_int("PDEGPU_TL_SMALL", 1) && nmax <= 288 && smem <= 227 * 1024) return PDEGPU_ERR_UNSUPPORTED;
+    }
+    return tline_run<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega, &a);
 }

@@ -70,6 +70,35 @@ class Steps:
         self._run(self.L.pdegpu_dev_llin_terms(self.ctx.h, ctypes.byref(t)))
         return tuple(_host(o, (nr, nc)) for o in out)
 
+    def llin_solve(self, d1, d2, U, V, dU, dV, b1, b2, alpha, gradmag, iters, omega, solver=2):
+        """pdegpu_dev_llin_solve: OPdiffWeights(U+dU, V+dV) + robust weights / channel sums + Oflow_sor_llin4_2d in one
+        call (fused into the line kernels' preparation where they run from packed lines). Returns the new (dU, dV)."""
+        nr, nc = dU.shape
+        t = lib.LlinTerms()
+        keep = []
+
+        def stack(x):
+            x = np.asarray(x, dtype=np.float32).reshape(nr, nc, -1)
+            keep.append(_dev(x))
+            return keep[-1].data_ptr(), x.shape[2]
+        for k, x in enumerate(d1):
+            t.d1[k], t.channels1 = stack(x)
+        t.channels2 = 0
+        if d2 is not None:
+            for k, x in enumerate(d2):
+                t.d2[k], t.channels2 = stack(x)
+        u, v, du, dv = _dev(U), _dev(V), _dev(dU), _dev(dV)
+        work = _empty(11 * nr * nc)
+        t.nrows, t.ncols, t.batch, t.gradmag = nr, nc, 1, 1 if gradmag else 0
+        t.b1, t.b2, t.alpha = b1, b2, alpha
+        t.batch_stride1, t.batch_stride2, t.batch_stride = nr * nc * t.channels1, nr * nc * max(t.channels2, 1), nr * nc
+        self.L.pdegpu_dev_llin_solve.restype = ctypes.c_int
+        self.L.pdegpu_dev_llin_solve.argtypes = [ctypes.c_void_p, ctypes.POINTER(lib.LlinTerms)] + [ctypes.c_void_p] * 5 + \
+            [ctypes.c_int, ctypes.c_float, ctypes.c_int]
+        self._run(self.L.pdegpu_dev_llin_solve(self.ctx.h, ctypes.byref(t), u.data_ptr(), v.data_ptr(), du.data_ptr(), dv.data_ptr(),
+                                               work.data_ptr(), iters, omega, solver))
+        return _host(du, (nr, nc)), _host(dv, (nr, nc))
+
     def elin_terms(self, der, coef, U, V, b1, b2, alpha, summed):
         nr, nc = U.shape
         t = lib.ElinTerms()

@@ -15,6 +15,13 @@ for p in (ROOT, PKG):
 # The suites written against the zebra / red-black kernels (generation cross-checks, throughput-shaped properties) pin
 # that order; tests/test_gpu_reference_order.py switches to "reference" / "auto" explicitly.
 os.environ.setdefault("PDEGPU_ORDER", "fast")
+# the fused weights + terms preparation of the late-linearisation inner solve is opt-in (slower than the separate kernels,
+# DESIGN.md section 4); the GPU suite runs WITH it so that the fused path is the one held to bitwise equality
+os.environ.setdefault("PDEGPU_FUSE", "1")
+# the temporally blocked point kernel (two sweeps per HBM pass) is chosen by the library only where it wins (>= 3 strips per
+# SM); the GPU suite forces it on so that every point-solver test, the generation cross-checks and the band tests hold
+# IT to bitwise equality with generation 0
+os.environ.setdefault("PDEGPU_POINT_WINDOW", "1")
 
 
 def pytest_configure(config):

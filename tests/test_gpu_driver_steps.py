@@ -4,6 +4,8 @@ restatement of the reference's .m formulas. Called through the C ABI (pdegpu_dev
 Tolerances: formulas evaluated in single by the drivers are restated with one rounding per operation on
 both sides -> bit-exact or 1e-6; double-precision formulas cast to single -> 1e-6 relative (north_star:
 "warps and pyramids must match within 1e-6", non-iterative kernels 1e-5)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,32 @@ def test_ad_diff_weights_and_tv_terms(steps, shape, frames):
     g1 = steps.ad_diff_weights(D)
     for k in range(8):
         assert close(g1[k], o[k].astype(np.float32), 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(96, 120), (203, 270), (37, 53)])
+@pytest.mark.parametrize("order", ["fast", "reference"])
+def test_fused_inner_solve_equals_the_three_steps(steps, shape, order):
+    """pdegpu_dev_llin_solve (FlowEminND_llin_2D_v10.m:278-348 in one call; weights and terms computed inside the line
+    kernels' preparation, north_star subsystem 3) against OPdiffWeights, the term assembly and Oflow_sor_llin4_2d called
+    one after the other: the same bits. (37 x 53 takes the shared-memory resident kernel: the unfused path inside.)
+    The fused preparation is opt-in (PDEGPU_FUSE=1, read once per process: set in tests/conftest.py)."""
+    from pdegpu import lib, mex
+    nr, nc = shape
+    r = np.random.default_rng(17)
+    c1, c2 = 6, 3
+    d1 = [(r.standard_normal((nr, nc, c1)) * 0.1).astype(np.float32) for _ in range(3)]
+    d2 = [(r.standard_normal((nr, nc, c2)) * 0.1).astype(np.float32) for _ in range(5)]
+    d1[0][3, 4, 1] = np.nan                                    # a warped pixel that left the image
+    U, V = synth.smooth_field(r, nr, nc, 2.0).astype(np.float32), synth.smooth_field(r, nr, nc, 2.0).astype(np.float32)
+    dU, dV = (0.05 * r.standard_normal((nr, nc))).astype(np.float32), (0.05 * r.standard_normal((nr, nc))).astype(np.float32)
+    steps.ctx.set_sweep_order(lib.ORDER_REFERENCE if order == "reference" else lib.ORDER_FAST)
+    os.environ["PDEGPU_ORDER"] = order
+    try:
+        fu, fv = steps.llin_solve(d1, d2, U, V, dU, dV, 1.4843, 0.2915, 0.042, True, 4, 1.9)
+        wW, wN, wS, wE = steps.op_diff_weights((U + dU).astype(np.float32), (V + dV).astype(np.float32))
+        M, Cu, Cv, Du, Dv = steps.llin_terms(d1, d2, dU, dV, 1.4843, 0.2915, 0.042, True)
+        su, sv = mex.Oflow_sor_llin4_2d(U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, np.float32(4), np.float32(1.9), np.float32(2))
+    finally:
+        os.environ["PDEGPU_ORDER"] = "fast"
+        steps.ctx.set_sweep_order(lib.ORDER_FAST)
+    assert np.array_equal(fu, su, equal_nan=True) and np.array_equal(fv, sv, equal_nan=True)
