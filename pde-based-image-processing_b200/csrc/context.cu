@@ -171,7 +171,7 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 int pdegpu_lane_count(pdegpu_ctx *ctx, int batch)
 {
-    static const int max_lanes = getenv("PDEGPU_LANES") ? atoi(getenv("PDEGPU_LANES")) : 16;
+    static const int max_lanes = getenv("PDEGPU_LANES") ? atoi(getenv("PDEGPU_LANES")) : 32;
     if (ctx->prof_on || ctx->parent || batch < 2 || max_lanes < 2) return 1;
     const int cap = (int)(sizeof(ctx->lanes) / sizeof(ctx->lanes[0]));
     int n = batch < max_lanes ? batch : max_lanes;

@@ -57,3 +57,68 @@ def test_tvdenoise8_4096x2160(ctx):
     assert out.shape == noisy.shape and np.isfinite(out).all()
     rm = lambda a: float(np.sqrt(np.mean((a - clean) ** 2)))
     assert rm(out) < 0.8 * rm(noisy), f"RMSE vs clean: {rm(out)} after, {rm(noisy)} before"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the same configurations AGAINST THE REFERENCE, in the reference's sweep order (round 2): at the full size where the CPU
+# side finishes in seconds (FMG at 1080p: 14 s), on a quarter-size crop where it does not
+# ------------------------------------------------------------------------------------------------------------------
+def _ref_backend():
+    from oracle import oracle as o
+    return o.RefBackend() if o.have_ref() else o.OracleBackend()
+
+
+@pytest.fixture()
+def ref_order_ctx(built):
+    from pdegpu import lib
+    c = lib.Context(0)
+    c.set_sweep_order(lib.ORDER_REFERENCE)
+    yield c
+    c.close()
+
+
+def test_fmg_1080p_equals_the_reference_driver(built):
+    """configs[2] at its full size, driver defaults, library defaults (PDEGPU_ORDER_AUTO -> reference order for this
+    driver): the flow of pdegpu_flow_fmg_2d against the restated .m driver on the unmodified reference MEX code"""
+    from oracle import pipelines
+    from pdegpu import lib
+    nr, nc = 1080, 1920
+    I0, I1, u, v = synth.image_pair(300, nr, nc, nframes=1, scale=255.0, max_flow=0.8)
+    c = lib.Context(0)
+    c.set_sweep_order(lib.ORDER_AUTO)
+    U, V = c.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1))
+    c.close()
+    Uo, Vo = pipelines.flow_fmg(I0.reshape(nr, nc, 1), I1.reshape(nr, nc, 1), _ref_backend())
+    e = float(np.mean(np.sqrt((U.astype(np.float64) - Uo) ** 2 + (V.astype(np.float64) - Vo) ** 2)))
+    assert np.isfinite(U).all() and e < 1e-3, f"mean EPE GPU vs reference FMG driver at 1080p: {e}"
+
+
+def test_symmetric_stereo_crop_equals_the_reference_driver(ref_order_ctx):
+    """configs[3], stereo half, 540 x 1024 (a quarter of 2160 x 4096 each way), driver defaults, reference order"""
+    from oracle import pipelines
+    nr, nc = 540, 1024
+    Il, Ir, u, _ = synth.image_pair(303, nr, nc, nframes=1, scale=255.0, max_flow=4.0 / 0.55, horizontal=True)
+    U0, U1 = ref_order_ctx.disp_sym(Il, Ir)
+    O0, O1 = pipelines.disp_sym(Il, Ir, _ref_backend())
+    assert np.array_equal(np.isnan(U0), np.isnan(O0)) and np.array_equal(np.isnan(U1), np.isnan(O1))
+    # The driver is ill-conditioned at a handful of pixels next to regions that left the image (NaN data terms, almost
+    # no diagonal): there BOTH sides return disparities of tens of pixels, which differ (measured, tools/disp_diag.py:
+    # median difference 1e-6 .. 3e-6 px at every size, single pixels up to 12 px at 135 x 256). So: the median, and the
+    # share of pixels that are off by more than a hundredth of a pixel.
+    for G, O in ((U0, O0), (U1, O1)):
+        d = np.abs(G - O)
+        assert float(np.nanmedian(d)) < 1e-5 and float(np.nanmean(d > 1e-2)) < 5e-3, (float(np.nanmedian(d)), float(np.nanmean(d > 1e-2)))
+
+
+def test_tvdenoise8_crop_equals_the_reference_driver(ref_order_ctx):
+    """configs[3], denoising half, 540 x 1024, reference order (PDEsolver8's line solver runs ONE iteration per call)"""
+    from oracle import pipelines
+    nr, nc = 540, 1024
+    rng = np.random.default_rng(304)
+    ii, jj = np.meshgrid(np.arange(nr), np.arange(nc), indexing="ij")
+    clean = (0.5 + 0.3 * np.sin(ii / 37.0) * np.cos(jj / 51.0)).astype(np.float32)
+    noisy = (clean + 0.08 * rng.standard_normal(clean.shape)).astype(np.float32)
+    g = ref_order_ctx.tvdenoise8(noisy, outer_iter=5)
+    o = pipelines.tvdenoise8(noisy, _ref_backend(), outer_iter=5)
+    rng_ = float(np.max(np.abs(o)))
+    assert float(np.mean(np.abs(g - o))) < 1e-4 * rng_ and float(np.max(np.abs(g - o))) < 5e-3 * rng_
