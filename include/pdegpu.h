@@ -77,7 +77,8 @@ int         pdegpu_profile_report(pdegpu_ctx *ctx, char *buf, size_t buflen);
 /* Kernel generation: 0 = "simple" global-memory kernels (kept as an in-library cross-check),
  * 1 = streaming register/shared-memory kernels (default). */
 int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);
-/* Order in which solver 2 (alternating line relaxation) visits the lines of a direction.
+/* Order in which the sweeps visit the unknowns: solver 2 (alternating line relaxation) the lines of a direction, solver 1
+ * (point relaxation) the pixels.
  *   PDEGPU_ORDER_FAST: zebra -- even lines, then odd lines; every line of a colour in parallel. Same fixed point as the
  *     reference, the HBM-bound kernel of the throughput numbers; its iterate after a FEW sweeps differs from the
  *     reference's (information travels two lines per sweep instead of across the image).
@@ -85,14 +86,17 @@ int         pdegpu_set_kernel_path(pdegpu_ctx *ctx, int path);
  *     (GS_ALR_SOR_*: opticalflowSolvers.c:196,690,1677; disparitySolvers.c:154; pdeSolvers.c:277,344). Iterates agree
  *     with the reference sweep by sweep (1e-5 of the field's range, tests/test_gpu_reference_order.py), so the unchanged
  *     .m drivers give the reference's flow at the reference's iteration counts. Serial from line to line: the
- *     parallelism is the batch (one CTA per problem, several per SM) and the lanes inside a line.
+ *     parallelism is the batch (one CTA per problem, several per SM) and the lanes inside a line. Solver 1 in this order
+ *     is the reference's lexicographic point Gauss-Seidel (for j, for i, in place), run as a wavefront over the
+ *     anti-diagonals of a problem.
  *   PDEGPU_ORDER_AUTO (default): REFERENCE for the early-linearisation flow family (PDEGPU_FLOW_ELIN4, i.e. the
  *     Horn-Schunck and FMG drivers, which solve each level ONCE and never re-warp: the iterate after `iter` sweeps is
  *     their result, and at their default iter = 20 / 4 the zebra iterate is a measurably different flow -- Yosemite
  *     FMG: 0.69 px against the reference's 0.21 px average end-point error); FAST for every other family (their
  *     drivers re-warp and re-linearise, both orders recover the ground truth equally well at the default settings).
  * The environment variable PDEGPU_ORDER = reference | fast | auto sets the initial order of a context; the MEX gateways
- * (which own their context) follow it at every call. Solver 1 (point relaxation) is not affected. Applies to
+ * (which own their context) follow it at every call. FAST for solver 1 is the red-black (8-neighbour: four-colour)
+ * order; AUTO never changes solver 1 (no driver uses it by default). Applies to
  * pdegpu_dev_relax and everything built on it (host-pointer entry points, driver pipelines). */
 #define PDEGPU_ORDER_FAST      0
 #define PDEGPU_ORDER_REFERENCE 1

@@ -37,6 +37,7 @@ extern "C" int pdegpu_dev_relax(pdegpu_ctx *ctx, const pdegpu_system *sys, int i
     if (solver != 1 && solver != 2) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "pdegpu_dev_relax: no such solver %d", solver);
     PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (iter <= 0 && !(sys->family == PDEGPU_PDE8 && solver == 2)) return PDEGPU_OK;
+    if (solver == 1 && ctx->sweep_order == PDEGPU_ORDER_REFERENCE) return relax_lexpoint(ctx, sys, iter, omega);
     if (solver == 2 && (ctx->sweep_order == PDEGPU_ORDER_REFERENCE ||
                         (ctx->sweep_order == PDEGPU_ORDER_AUTO && sys->family == PDEGPU_FLOW_ELIN4)))
         return relax_lexline(ctx, sys, iter, omega);

@@ -149,6 +149,7 @@ template <int FAM> constexpr double sweep_bytes()
 // ------------------------------------------------------------------------------------------
 int relax_simple(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);
 int relax_llin_fused(pdegpu_ctx *ctx, const pdegpu_system *sys, const struct pdegpu_llin_terms *t, int iter, float omega, bool reference_order);   // sweeps_tline.cu
+int relax_lexpoint(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega);               // solver 1 in the reference's lexicographic order (sweeps_simple.cu)
 int relax_lexline(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega);                // solver 2 in the reference's line order (sweeps_tline.cu)
 int relax_stream(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver);   // returns PDEGPU_ERR_UNSUPPORTED when it has no kernel for the case
 

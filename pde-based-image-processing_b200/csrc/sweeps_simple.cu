@@ -177,6 +177,69 @@ static int run_family(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float
     return solver == 1 ? run_point<FAM>(ctx, sys, iter, omega) : run_line<FAM>(ctx, sys, iter, omega);
 }
 
+// ---------------------------------------------------------------------------------------------
+// solver 1 in the REFERENCE'S ORDER (pdegpu_set_sweep_order(ctx, PDEGPU_ORDER_REFERENCE)): lexicographic point
+// Gauss-Seidel -- for j, for i, in place (GS_SOR_elin4_2d opticalflowSolvers.c:89-158, GS_SOR_llin4_2d :563-655,
+// disparitySolvers.c:89-125, pdeSolvers.c:94-125, :208-247), border fill after every sweep. Pixel (i, j) sees the new
+// (i-1, j) and (i, j-1) [8-neighbour: also the new (i-1, j-1) and (i+1, j-1)] and old values elsewhere: all pixels with
+// the same i + j (8-neighbour: i + 2j) are independent, so a CTA walks the anti-diagonals of one problem with a barrier
+// between them. The parallelism is the batch and the length of a diagonal; same point_update as generation 0.
+// ---------------------------------------------------------------------------------------------
+template <int FAM>
+__global__ void __launch_bounds__(512)
+lex_point_kernel(SysView s, int iter, float omega)
+{
+    constexpr int S = (Fam<FAM>::PDE && Fam<FAM>::EIGHT) ? 2 : 1;
+    constexpr int NUNK = Fam<FAM>::NUNK;
+    const int nr = s.nrows, nc = s.ncols;
+    const long long base = (long long)blockIdx.x * s.bstride;
+    const int per = 2 * nr + 2 * nc;
+    for (int it = 0; it < iter; it++) {
+        for (int d = 1 + S; d <= (nr - 2) + S * (nc - 2); d++) {
+            // i + S j = d with 1 <= i <= nr-2, 1 <= j <= nc-2
+            const int jlo = max(1, (d - (nr - 2) + S - 1) / S), jhi = min(nc - 2, (d - 1) / S);
+            for (int j = jlo + threadIdx.x; j <= jhi; j += blockDim.x)
+                point_update<FAM>(s, base + (long long)j * nr + (d - S * j), omega);
+            __syncthreads();
+        }
+        for (int t = threadIdx.x; t < per; t += blockDim.x) {         // border pixel := nearest interior pixel
+            int i, j;
+            if (t < nr)               { i = t;            j = 0; }
+            else if (t < 2 * nr)      { i = t - nr;       j = nc - 1; }
+            else if (t < 2 * nr + nc) { i = 0;            j = t - 2 * nr; }
+            else                      { i = nr - 1;       j = t - 2 * nr - nc; }
+            const int ic = min(max(i, 1), nr - 2), jc = min(max(j, 1), nc - 2);
+#pragma unroll
+            for (int q = 0; q < NUNK; q++) s.x[q][base + (long long)j * nr + i] = s.x[q][base + (long long)jc * nr + ic];
+        }
+        __syncthreads();
+    }
+}
+
+template <int FAM>
+static int run_lex_point(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    if (iter <= 0) return PDEGPU_OK;
+    SysView v = make_view(sys);
+    PDEGPU_PROF(ctx, "lex_point_kernel", sweep_bytes<FAM>() * (double)sys->nrows * sys->ncols * sys->batch * iter);
+    lex_point_kernel<FAM><<<sys->batch, 512, 0, ctx->stream>>>(v, iter, omega);
+    PDEGPU_LAUNCH_CHECK(ctx, "lex_point_kernel");
+    return PDEGPU_OK;
+}
+
+int relax_lexpoint(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega)
+{
+    switch (sys->family) {
+    case PDEGPU_FLOW_ELIN4: return run_lex_point<PDEGPU_FLOW_ELIN4>(ctx, sys, iter, omega);
+    case PDEGPU_FLOW_LLIN4:
+    case PDEGPU_FLOW_LLIN8: return run_lex_point<PDEGPU_FLOW_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_DISP_LLIN4: return run_lex_point<PDEGPU_DISP_LLIN4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE4:       return run_lex_point<PDEGPU_PDE4>(ctx, sys, iter, omega);
+    case PDEGPU_PDE8:       return run_lex_point<PDEGPU_PDE8>(ctx, sys, iter, omega);
+    default: return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "relax: unknown family %d", sys->family);
+    }
+}
+
 int relax_simple(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, int solver)
 {
     switch (sys->family) {
