@@ -32,6 +32,7 @@ struct LexParams {
     int n, nlines;
     int Mr;                        // elements per lane (odd)
     int KS, RL;                    // coefficient slabs, ring lines
+    int inslab;                    // long lines: the eliminated rows live in the slab rows only their solver warp reads (see the kernel)
     int skip_border;               // 8-neighbour PDE: first and last line of a problem are not relaxed
     float omega;
 };
@@ -52,7 +53,7 @@ __device__ __forceinline__ float lex_rcp(float x)
 // is the producer. Two chains of dependent line solves overlap instead of one chain of twice the length.
 template <int NUNK> struct LexThreads { static constexpr int value = 32 * (NUNK + 1); };
 
-template <int NUNK, int NN, int MODE>
+template <int NUNK, int NN, int MODE, bool INSLAB>
 __global__ void __launch_bounds__(LexThreads<NUNK>::value)
 lex_pass_kernel(const LexParams p)
 {
@@ -66,8 +67,14 @@ lex_pass_kernel(const LexParams p)
     const int TP = NUNK * P;                                  // floats per ring entry
     float *ring = smem;
     float *slabs = ring + (size_t)RL * TP;
-    float4 *rowsAll = reinterpret_cast<float4 *>(slabs + (size_t)KS * NC * P);   // per solver warp: eliminated rows (spike, super-diagonal, rhs)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(rowsAll + (size_t)NUNK * 32 * Mr);
+    // per solver warp: the eliminated rows (spike, super-diagonal, right-hand side), one float4 per element. LONG LINES
+    // (inslab): two slabs + ring + 16 bytes per element and unknown do not fit 227 KB at 1920 elements, and with ONE slab
+    // the second solver warp cannot overlap with the first (it works one line = one slab behind). There the super-diagonal
+    // and the right-hand side overwrite the slab rows C_q, D_q -- read by solver warp q only, once per element, just
+    // before -- and only the spike keeps a 4-byte scratch: two slabs fit again.
+    constexpr bool inslab = INSLAB;                           // (compile time: a run-time flag in the three row loops cost 45 %)
+    float4 *rowsAll = reinterpret_cast<float4 *>(slabs + (size_t)KS * NC * P);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<float *>(rowsAll) + (size_t)NUNK * 32 * Mr * (inslab ? 1 : 4));
     uint64_t *sfull = bars, *sempty = bars + KS, *rfull = bars + 2 * KS, *rempty = bars + 2 * KS + RL;
     unsigned *first_done = reinterpret_cast<unsigned *>(bars + 2 * KS + 2 * RL);   // lines the first solver warp has finished
 
@@ -113,7 +120,8 @@ lex_pass_kernel(const LexParams p)
     // ========================================= solver warps =========================================
     const int q = warp;                                       // 0: the unknown solved first, 1: the second
     const bool last_solver = q == NUNK - 1;                   // writes the finished line back
-    float4 *rows = rowsAll + (size_t)q * 32 * Mr;
+    float4 *rows = rowsAll + (size_t)q * 32 * Mr;                                   // (not inslab)
+    float *spike = reinterpret_cast<float *>(rowsAll) + (size_t)q * 32 * Mr;        // (inslab)
     const float omega = p.omega, om1 = 1.0f - p.omega;
     const int o = lane * Mr;
     const int t0 = (NUNK == 2 ? p.q0 : 0) * P, t1 = (NUNK == 2 ? (p.q0 ^ 1) : 0) * P;
@@ -127,6 +135,16 @@ lex_pass_kernel(const LexParams p)
         const float *lo = eLo ? ring + (size_t)((j - 1) % RL) * TP : own;
         const float *hi = eHi ? ring + (size_t)((j + 1) % RL) * TP : own;
         const float *sl = slabs + (size_t)ks * NC * P;
+        float *slw = slabs + (size_t)ks * NC * P;             // (inslab: rows cq, dq are this warp's to overwrite)
+        auto row_put = [&](int e, float a_, float b_, float d_) {
+            if (!inslab) rows[e] = make_float4(a_, b_, d_, 0.f);
+            else if (e < n) { spike[e] = a_; slw[cq * P + e] = b_; slw[dq * P + e] = d_; }
+        };
+        auto row_get = [&](int e) -> float4 {                 // (.x spike, .y super-diagonal, .z right-hand side)
+            if (!inslab) return rows[e];
+            if (e < n) return make_float4(spike[e], slw[cq * P + e], slw[dq * P + e], 0.f);
+            return make_float4(0.f, 0.f, 0.f, 0.f);           // identity rows past the end of the line
+        };
         mbar_wait(&sfull[ks], (unsigned)(j / KS) & 1u);
         mbar_wait(&rfull[rs], (unsigned)(j / RL) & 1u);
         if (eHi) mbar_wait(&rfull[(j + 1) % RL], (unsigned)((j + 1) / RL) & 1u);
@@ -176,16 +194,16 @@ lex_pass_kernel(const LexParams p)
                 const float an = k == 0 ? a * inv : (-a * ap) * inv;
                 const float dn = k == 0 ? d * inv : (d - a * dp) * inv;
                 bp = c * inv; ap = an; dp = dn;
-                rows[e] = make_float4(ap, bp, dp, 0.f);
+                row_put(e, ap, bp, dp);
             }
             // ---- first unknown of the chunk in terms of the last one and x_left
             float Af, Bf, Gf;
             if (Mr == 1) { Af = 0.f; Bf = -1.0f; Gf = 0.f; }
             else {
-                const float4 r0 = rows[o + Mr - 2];
+                const float4 r0 = row_get(o + Mr - 2);
                 Af = r0.z; Bf = r0.y; Gf = r0.x;
                 for (int r = Mr - 3; r >= 0; r--) {
-                    const float4 rr = rows[o + r];
+                    const float4 rr = row_get(o + r);
                     Af = rr.z - rr.y * Af;
                     Bf = -rr.y * Bf;
                     Gf = rr.x - rr.y * Gf;
@@ -216,7 +234,7 @@ lex_pass_kernel(const LexParams p)
             float x = l;
             for (int r = Mr - 1; r >= 0; r--) {
                 const int e = o + r;
-                if (r < Mr - 1) { const float4 rr = rows[e]; x = rr.z - rr.y * x - rr.x * L; }
+                if (r < Mr - 1) { const float4 rr = row_get(e); x = rr.z - rr.y * x - rr.x * L; }
                 if (e < n) own[tq + e] = omega * x + om1 * own[tq + e];
             }
         }

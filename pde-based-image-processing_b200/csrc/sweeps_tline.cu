@@ -510,18 +510,21 @@ int tline_small_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float o
 // pass in place on the column-layout T lines, their transposition, the row pass in place, the transposition back; the
 // increment is recovered as in the zebra path.
 // ------------------------------------------------------------------------------------------------------------------
-struct LexGeom { int Mr, KS, RL; size_t smem; };
+struct LexGeom { int Mr, KS, RL, inslab; size_t smem; };
 
 static bool lex_geometry(int n, int nunk, int nc, LexGeom &g)
 {
     const int P = (n + 3) & ~3;
     g.Mr = ((n + 31) / 32) | 1;
     const size_t room = 227 * 1024;
-    const size_t slab = (size_t)nc * P * 4, line = (size_t)nunk * P * 4, scratch = (size_t)nunk * 32 * g.Mr * 16;
-    const int cand[][2] = {{2, 5}, {2, 4}, {2, 3}, {1, 4}, {1, 3}};
+    const size_t slab = (size_t)nc * P * 4, line = (size_t)nunk * P * 4;
+    // (slabs, ring lines, eliminated rows inside the slab): two slabs first -- with one the two solver warps of a flow
+    // family cannot overlap -- then the roomier ring
+    const int cand[][3] = {{2, 5, 0}, {2, 4, 0}, {2, 3, 0}, {2, 4, 1}, {2, 3, 1}, {1, 4, 0}, {1, 3, 0}, {1, 3, 1}};
     for (auto &c : cand) {
+        const size_t scratch = (size_t)nunk * 32 * g.Mr * (c[2] ? 4 : 16);
         const size_t need = c[0] * slab + c[1] * line + scratch + (size_t)(2 * c[0] + 2 * c[1]) * 8 + 128;
-        if (need <= room) { g.KS = c[0]; g.RL = c[1]; g.smem = need; return true; }
+        if (need <= room) { g.KS = c[0]; g.RL = c[1]; g.inslab = c[2]; g.smem = need; return true; }
     }
     return false;
 }
@@ -532,11 +535,13 @@ int lex_pass(pdegpu_ctx *ctx, LexParams &p, int batch, double bytes, const char 
     constexpr int NC = 6 + (NUNK == 2 ? 3 : 0) + (NN == 8 ? 4 : 0);
     LexGeom g;
     if (!lex_geometry(p.n, NUNK, NC, g)) return PDEGPU_ERR_UNSUPPORTED;
-    p.Mr = g.Mr; p.KS = g.KS; p.RL = g.RL;
-    cudaError_t e = cudaFuncSetAttribute(lex_pass_kernel<NUNK, NN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    p.Mr = g.Mr; p.KS = g.KS; p.RL = g.RL; p.inslab = g.inslab;
+    cudaError_t e = g.inslab ? cudaFuncSetAttribute(lex_pass_kernel<NUNK, NN, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(lex_pass_kernel<NUNK, NN, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaFuncSetAttribute(lex_pass_kernel)");
     PDEGPU_PROF(ctx, name, bytes);
-    lex_pass_kernel<NUNK, NN, MODE><<<batch, LexThreads<NUNK>::value, g.smem, ctx->stream>>>(p);
+    if (g.inslab) lex_pass_kernel<NUNK, NN, MODE, true><<<batch, LexThreads<NUNK>::value, g.smem, ctx->stream>>>(p);
+    else          lex_pass_kernel<NUNK, NN, MODE, false><<<batch, LexThreads<NUNK>::value, g.smem, ctx->stream>>>(p);
     PDEGPU_LAUNCH_CHECK(ctx, "lex_pass_kernel");
     return PDEGPU_OK;
 }
