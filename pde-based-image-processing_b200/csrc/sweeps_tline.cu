@@ -131,22 +131,25 @@ struct FinalParams { float *x[2]; const float *x0[2]; const float *tn; int nunk;
 static __global__ void __launch_bounds__(256)
 tline_final_kernel(const FinalParams p)
 {
-    const int b = blockIdx.z, j = blockIdx.y;
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i >= p.nrows) return;
+    // one thread per 4 consecutive rows of one column (every thread of a block has work, whatever nrows is)
+    const int b = blockIdx.y;
+    const int n4 = (p.nrows + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n4 * p.ncols) return;
+    const int j = (int)(t / n4), i = (int)(t - (long long)j * n4) * 4;
     const long long d = (long long)b * p.xbs + (long long)j * p.nrows + i;
     const int seg0 = i / p.ns0, io = i - seg0 * p.ns0;
     for (int q = 0; q < p.nunk; q++) {
-        const float *t = p.tn + ((((long long)b * p.S0 + seg0) * p.ncols + j) * p.nunk + q) * p.pitch0 + io;
+        const float *t_ = p.tn + ((((long long)b * p.S0 + seg0) * p.ncols + j) * p.nunk + q) * p.pitch0 + io;
         if (p.vec) {                                          // 16-byte aligned caller arrays, lines a multiple of 4 long
-            float4 v = *reinterpret_cast<const float4 *>(t);
+            float4 v = *reinterpret_cast<const float4 *>(t_);
             if (p.x0[q]) {
                 const float4 u = *reinterpret_cast<const float4 *>(p.x0[q] + d);
                 v.x -= u.x; v.y -= u.y; v.z -= u.z; v.w -= u.w;
             }
             *reinterpret_cast<float4 *>(p.x[q] + d) = v;
         } else {
-            for (int k = 0; k < 4 && i + k < p.nrows; k++) p.x[q][d + k] = t[k] - (p.x0[q] ? p.x0[q][d + k] : 0.f);
+            for (int k = 0; k < 4 && i + k < p.nrows; k++) p.x[q][d + k] = t_[k] - (p.x0[q] ? p.x0[q][d + k] : 0.f);
         }
     }
 }
@@ -342,7 +345,7 @@ int tline_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, 
         bool vec = (nr % 4 == 0) && (sys->batch_stride % 4 == 0);
         for (int q = 0; q < NUNK; q++) vec = vec && (((uintptr_t)sys->x[q] | (uintptr_t)(F::LATE ? sys->x0[q] : nullptr)) & 15) == 0;
         fp.vec = vec ? 1 : 0;
-        dim3 grid((nr + 1023) / 1024, nc, batch);
+        dim3 grid((unsigned)(((long long)((nr + 3) / 4) * nc + 255) / 256), batch);
         PDEGPU_PROF(ctx, "tline_final_kernel", 4.0 * NUNK * (F::LATE ? 3 : 2) * nr * nc * batch);
         tline_final_kernel<<<grid, 256, 0, ctx->stream>>>(fp);
         PDEGPU_LAUNCH_CHECK(ctx, "tline_final_kernel");
@@ -616,7 +619,7 @@ int lex_run(pdegpu_ctx *ctx, const pdegpu_system *sys, int iter, float omega, co
         bool vec = (nr % 4 == 0) && (sys->batch_stride % 4 == 0);
         for (int q = 0; q < NUNK; q++) vec = vec && (((uintptr_t)sys->x[q] | (uintptr_t)(F::LATE ? sys->x0[q] : nullptr)) & 15) == 0;
         fp.vec = vec ? 1 : 0;
-        dim3 grid((nr + 1023) / 1024, nc, batch);
+        dim3 grid((unsigned)(((long long)((nr + 3) / 4) * nc + 255) / 256), batch);
         PDEGPU_PROF(ctx, "tline_final_kernel", 0);
         tline_final_kernel<<<grid, 256, 0, ctx->stream>>>(fp);
         PDEGPU_LAUNCH_CHECK(ctx, "tline_final_kernel");
