@@ -438,12 +438,19 @@ def device_system(torch, dev, fam, nr, nc, batch, seed):
     ix, iy, it = r(-0.5, 1), r(-0.5, 1), r(-0.5, 1)
     gd = torch.clamp(1.0 / torch.sqrt(it * it + 1e-5), max=50.0)
     nan = torch.rand(shape, device=dev, generator=g) < 0.01
-    if fam in ("elin4", "llin4"):
+    if fam in ("elin4", "llin4", "llin8"):
         f.update({"M": gd * ix * iy, "Cu": -gd * it * ix, "Cv": -gd * it * iy, "Du": gd * ix * ix, "Dv": gd * iy * iy})
         for k in ("M", "Cu", "Cv", "Du", "Dv"):
             f[k][nan] = float("nan")
         f["U"], f["V"] = r(-2, 4), r(-2, 4)
         f["dU"], f["dV"] = r(-0.05, 0.1), r(-0.05, 0.1)
+        if fam == "llin8":                        # small diagonal weights of either sign, edge-symmetric (ADdiffWeights' dxy terms)
+            dg, da = r(-0.1, 0.2), r(-0.1, 0.2)
+            f["wSE"] = dg.clone(); f["wSE"][:, -1, :] = 0; f["wSE"][:, :, -1] = 0
+            f["wNW"] = torch.zeros_like(dg); f["wNW"][:, 1:, 1:] = dg[:, :-1, :-1]
+            f["wNE"] = da.clone(); f["wNE"][:, -1, :] = 0; f["wNE"][:, :, 0] = 0
+            f["wSW"] = torch.zeros_like(da); f["wSW"][:, 1:, :-1] = da[:, :-1, 1:]
+            del dg, da
     elif fam == "disp":
         f.update({"Cu": -gd * it * ix, "Du": gd * ix * ix})
         f["Cu"][nan] = float("nan"); f["Du"][nan] = float("nan")
@@ -471,6 +478,11 @@ def device_sysd(lib, fam, f, nr, nc, batch):
     if fam == "elin4":
         return lib.make_system(lib.FLOW_ELIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(), f["dV"].data_ptr()),
                                m=f["M"].data_ptr(), c=(f["Cu"].data_ptr(), f["Cv"].data_ptr()), d=(f["Du"].data_ptr(), f["Dv"].data_ptr()), w=w), ("dU", "dV")
+    if fam == "llin8":
+        w8 = w + [f[k].data_ptr() for k in ("wNW", "wNE", "wSE", "wSW")]
+        return lib.make_system(lib.FLOW_LLIN8, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(), f["dV"].data_ptr()),
+                               x0=(f["U"].data_ptr(), f["V"].data_ptr()), m=f["M"].data_ptr(), c=(f["Cu"].data_ptr(), f["Cv"].data_ptr()),
+                               d=(f["Du"].data_ptr(), f["Dv"].data_ptr()), w=w8), ("dU", "dV")
     if fam == "llin4":
         return lib.make_system(lib.FLOW_LLIN4, nr, nc, batch=batch, batch_stride=n, x=(f["dU"].data_ptr(), f["dV"].data_ptr()),
                                x0=(f["U"].data_ptr(), f["V"].data_ptr()), m=f["M"].data_ptr(), c=(f["Cu"].data_ptr(), f["Cv"].data_ptr()),
@@ -492,6 +504,7 @@ SWEEP_LEGS = [
     ("sweep_4096x2160", "Disp_sor_llin_sym4_2d = two Disp llin4 systems (finest level of configs[3], DispEminND_llin_sym_2D.m:227-246)", "disp", 2160, 4096, 4, 2, 4, 1.9, 36.0),
     ("sweep_tv_4096x2160", "PDEsolver4 (TVdenoise4.m:85-90 at the configs[3] image size)", "pde4", 2160, 4096, 4, 2, 4, 1.75, 32.0),
     ("tv8_4096x2160", "PDEsolver8 (TVdenoise8.m:87-100 at the configs[3] image size; ONE line iteration per call, SURVEY Q4)", "pde8", 2160, 4096, 4, 2, 1, 1.75, 48.0),
+    ("sweep_llin8_480x640", "Oflow_sor_llin8_2d (the 8-neighbour flow system of FlowEminAD_llin_2D_v10.m:357-377)", "llin8", 480, 640, 32, 2, 4, 1.9, 76.0),
     ("point_480x640", "Oflow_sor_llin4_2d solver 1 (red-black point SOR)", "llin4", 480, 640, 64, 1, 4, 1.9, 60.0),
     ("point_window_480x640", "Oflow_sor_llin4_2d solver 1, temporally blocked: TWO sweeps per pass over HBM (rb_window_kernel, 148 problems = 5 strips per SM)", "llin4", 480, 640, 148, 1, 4, 1.9, 60.0),
     # the reference's own line order (one CTA per problem, three problems per SM): latency-bound by construction, quoted

@@ -100,14 +100,14 @@ lex_pass_kernel(const LexParams p)
             bulk_g2s(ring, tg, tbytes, &rfull[0]);
             for (int j = 0; j < nlines; j++) {
                 const int ks = j % KS;
-                if (j >= KS) mbar_wait(&sempty[ks], (unsigned)(j / KS - 1) & 1u);
+                if (j >= KS) mbar_wait_lazy(&sempty[ks], (unsigned)(j / KS - 1) & 1u);
                 fence_proxy_async();
                 mbar_expect_tx(&sfull[ks], sbytes);
                 bulk_g2s(slabs + (size_t)ks * NC * P, coef + (long long)j * NC * P, sbytes, &sfull[ks]);
                 const int g = j + 1;
                 if (g < nlines) {
                     const int rs = g % RL;
-                    if (g >= RL) mbar_wait(&rempty[rs], (unsigned)(g / RL - 1) & 1u);
+                    if (g >= RL) mbar_wait_lazy(&rempty[rs], (unsigned)(g / RL - 1) & 1u);
                     fence_proxy_async();
                     mbar_expect_tx(&rfull[rs], tbytes);
                     bulk_g2s(ring + (size_t)rs * TP, tg + (long long)g * TP, tbytes, &rfull[rs]);

@@ -524,6 +524,12 @@ static bool lex_geometry(int n, int nunk, int nc, LexGeom &g)
     // (slabs, ring lines, eliminated rows inside the slab): two slabs first -- with one the two solver warps of a flow
     // family cannot overlap -- then the roomier ring
     const int cand[][3] = {{2, 5, 0}, {2, 4, 0}, {2, 3, 0}, {2, 4, 1}, {2, 3, 1}, {1, 4, 0}, {1, 3, 0}, {1, 3, 1}};
+    static const int eKS = env_int("PDEGPU_LEX_KS", 0), eRL = env_int("PDEGPU_LEX_RL", 0);
+    if (eKS > 0 && eRL >= 3) {                                 // (tuning override)
+        const size_t scratch = (size_t)nunk * 32 * g.Mr * 16;
+        const size_t need = eKS * slab + eRL * line + scratch + (size_t)(2 * eKS + 2 * eRL) * 8 + 128;
+        if (need <= room) { g.KS = eKS; g.RL = eRL; g.inslab = 0; g.smem = need; return true; }
+    }
     for (auto &c : cand) {
         const size_t scratch = (size_t)nunk * 32 * g.Mr * (c[2] ? 4 : 16);
         const size_t need = c[0] * slab + c[1] * line + scratch + (size_t)(2 * c[0] + 2 * c[1]) * 8 + 128;

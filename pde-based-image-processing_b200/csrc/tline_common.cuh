@@ -74,6 +74,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t *b, unsigned parity)
     unsigned spins = 0;
     while (!mbar_try(b, parity)) if (++spins > (1u << 22)) __trap();
 }
+// The same for a thread that has nothing else to do (a producer far ahead of its consumers): it sleeps between polls
+// instead of re-issuing try_wait back to back, which costs its scheduler issue slots the solver warps could use.
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t *b, unsigned parity)
+{
+    unsigned spins = 0;
+    while (!mbar_try(b, parity)) {
+        __nanosleep(256);
+        if (++spins > (1u << 22)) __trap();
+    }
+}
 // 1-D bulk copy global -> shared through the TMA unit; completion is counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-OUT=gpurun_out/r3d
+OUT=gpurun_out/r3g
 mkdir -p $OUT
 date +%s > $OUT/t0
 timeout 1800 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.txt 2>&1
