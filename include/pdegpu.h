@@ -142,6 +142,23 @@ int pdegpu_oflow_sor_llin4_2d(pdegpu_ctx *ctx,
         const float *wW, const float *wN, const float *wE, const float *wS,
         int nrows, int ncols, int nframes, float iter, float omega, int solver);
 
+/* Batched, pipelined form of the two gateways above (no reference counterpart: the reference solves one system per MEX
+ * call, Oflow_sor_llin4_2d.c:355-361; a caller with many frame pairs -- BASELINE configs[4] -- loops over them). `batch`
+ * independent systems per call, system b of EVERY array at element offset b*nrows*ncols, channel 0 only, no residual
+ * outputs. The systems travel in chunks on parallel streams, so the upload of one chunk, the sweeps of the previous
+ * one and the download of the one before overlap: the call runs at PCIe speed instead of copy + sweep + copy.
+ * Results are bitwise those of `batch` single calls. PDEGPU_HOST_CHUNK / PDEGPU_HOST_LANES override the chunking. */
+int pdegpu_oflow_sor_elin4_2d_batch(pdegpu_ctx *ctx, float *U_out, float *V_out,
+        const float *U, const float *V, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int batch, float iter, float omega, int solver);
+int pdegpu_oflow_sor_llin4_2d_batch(pdegpu_ctx *ctx, float *dU_out, float *dV_out,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int batch, float iter, float omega, int solver);
+
 /* [dU dV] = Oflow_sor_llin8_2d(U,V,dU,dV,M,Cu,Cv,Du,Dv,wW,wNW,wN,wNE,wE,wSE,wS,wSW,iter,omega,solver)
  * replaces mex/source/Oflow_sor_llin8_2d.c (GS_SOR_llin8_2d opticalflowSolvers.c:1487 -- which
  * ignores the diagonal weights, SURVEY Q6 -- and GS_ALR_SOR_llin8_2d :1677). */

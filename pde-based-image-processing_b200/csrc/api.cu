@@ -144,9 +144,11 @@ struct HostCall {
         cudaError_t e = cudaMemcpyAsync(h, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
         if (e != cudaSuccess) rc = pdegpu_check_cuda(ctx, e, "cudaMemcpyAsync(D2H)");
     }
+    bool defer = false;              // batched entry points: the caller synchronises the lanes once at the end
     int finish()
     {
         if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+        if (defer) return PDEGPU_OK;
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) return pdegpu_check_cuda(ctx, e, "cudaStreamSynchronize");
         return PDEGPU_OK;
@@ -179,18 +181,22 @@ static int flow_sor4(pdegpu_ctx *ctx, const char *who, int family,
                      const float *U, const float *V, const float *dU, const float *dV, const float *M,
                      const float *Cu, const float *Cv, const float *Du, const float *Dv,
                      const float *wW, const float *wN, const float *wE, const float *wS,
-                     int nrows, int ncols, int nframes, float iter, float omega, int solver)
+                     int nrows, int ncols, int nframes, float iter, float omega, int solver,
+                     int batch = 1, bool defer = false)
 {
     int rc = check_host(ctx, who, nrows, ncols, nframes, solver, true);
     if (rc) return rc;
     const bool late = family == PDEGPU_FLOW_LLIN4;
     const bool want_res = RU && RV;
-    const size_t n = (size_t)nrows * ncols, nf = want_res ? n * nframes : n;   // data terms: all frames only for residuals
+    if (want_res && batch != 1) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: residuals of a batch are not supported", who);
+    // `batch` systems one after the other in every array (n = all of them)
+    const size_t n = (size_t)nrows * ncols * batch, nf = want_res ? n * nframes : n;   // data terms: all frames only for residuals
     const int it = (int)iter;
     HostCall hc(ctx, (late ? 4 : 2) * n + 5 * nf + 4 * n + 2 * n + (want_res ? 2 * nf : 0), 20);
+    hc.defer = defer;
     pdegpu_system s;
     memset(&s, 0, sizeof(s));
-    s.family = family; s.nrows = nrows; s.ncols = ncols; s.batch = 1; s.batch_stride = (long long)n;
+    s.family = family; s.nrows = nrows; s.ncols = ncols; s.batch = batch; s.batch_stride = (long long)nrows * ncols;
     // the unknowns of the residual are the INPUTS (Oflow_sor_elin4_2d.c:350); the sweep works on a copy
     float *xin0 = hc.in(late ? dU : U, n), *xin1 = hc.in(late ? dV : V, n);
     if (late) { s.x0[0] = hc.in(U, n); s.x0[1] = hc.in(V, n); }
@@ -244,6 +250,75 @@ extern "C" int pdegpu_oflow_sor_llin4_2d(pdegpu_ctx *ctx,
     NULLCHECK("pdegpu_oflow_sor_llin4_2d", dU_out, dV_out, U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS);
     return flow_sor4(ctx, "pdegpu_oflow_sor_llin4_2d", PDEGPU_FLOW_LLIN4, dU_out, dV_out, RU, RV,
                      U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, nrows, ncols, nframes, iter, omega, solver);
+}
+
+// Batched, pipelined form of the two 4-neighbour flow gateways: `batch` independent systems per call, every array holding
+// them one after the other. The systems go to the device in chunks on the context's lanes (own stream + arena each), so
+// the upload of chunk k+1, the sweeps of chunk k and the download of chunk k-1 overlap; one synchronisation at the end.
+static int flow_sor4_batch(pdegpu_ctx *ctx, const char *who, int family, float *o0, float *o1,
+                           const float *U, const float *V, const float *dU, const float *dV, const float *M,
+                           const float *Cu, const float *Cv, const float *Du, const float *Dv,
+                           const float *wW, const float *wN, const float *wE, const float *wS,
+                           int nrows, int ncols, int batch, float iter, float omega, int solver)
+{
+    int rc = check_host(ctx, who, nrows, ncols, 1, solver, true);
+    if (rc) return rc;
+    if (batch < 1) return pdegpu_set_error(ctx, PDEGPU_ERR_SHAPE, "%s: batch < 1", who);
+    if (ctx->parent) return pdegpu_set_error(ctx, PDEGPU_ERR_ARG, "%s: not callable on a lane", who);
+    PDEGPU_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const char *e_chunk = getenv("PDEGPU_HOST_CHUNK"), *e_lanes = getenv("PDEGPU_HOST_LANES");
+    const int env_chunk = e_chunk ? atoi(e_chunk) : 0, env_lanes = e_lanes && atoi(e_lanes) > 0 ? atoi(e_lanes) : 3;
+    const size_t n = (size_t)nrows * ncols;
+    // chunks of ~64 MB of operands: large enough for full-rate copies and full-width kernels, small enough that the
+    // first upload and the last download (the only parts that do not overlap) are a small share of the call
+    int chunk = env_chunk > 0 ? env_chunk : (int)((size_t)(4u << 20) / n);
+    if (chunk > (batch + 3) / 4) chunk = (batch + 3) / 4;
+    if (chunk < 1) chunk = 1;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    int nl = env_lanes < 1 ? 1 : (env_lanes > 8 ? 8 : env_lanes);
+    if (nl > nchunks) nl = nchunks;
+    if ((rc = pdegpu_lanes_prepare(ctx, nl, 0, who))) return rc;
+    PDEGPU_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));       // earlier work of this context (the lanes do not wait on events)
+    for (int c = 0; c < nchunks && !rc; c++) {
+        pdegpu_ctx *l = ctx->lanes[c % nl];
+        const size_t o = (size_t)c * chunk * n;
+        const int nb = (c + 1) * chunk <= batch ? chunk : batch - c * chunk;
+        rc = flow_sor4(l, who, family, o0 + o, o1 + o, nullptr, nullptr, U + o, V + o, dU ? dU + o : nullptr, dV ? dV + o : nullptr,
+                       M + o, Cu + o, Cv + o, Du + o, Dv + o, wW + o, wN + o, wE + o, wS + o,
+                       nrows, ncols, 1, iter, omega, solver, nb, true);
+        if (rc) memcpy(ctx->err, l->err, sizeof ctx->err);
+    }
+    for (int k = 0; k < nl; k++) {
+        pdegpu_ctx *l = ctx->lanes[k];
+        cudaError_t e = cudaStreamSynchronize(l->stream);
+        if (e != cudaSuccess && !rc) rc = pdegpu_check_cuda(ctx, e, "cudaStreamSynchronize(lane)");
+        ctx->launches += l->launches; l->launches = 0;
+    }
+    return rc;
+}
+
+extern "C" int pdegpu_oflow_sor_elin4_2d_batch(pdegpu_ctx *ctx, float *U_out, float *V_out,
+        const float *U, const float *V, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int batch, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_sor_elin4_2d_batch", U_out, V_out, U, V, M, Cu, Cv, Du, Dv, wW, wN, wE, wS);
+    return flow_sor4_batch(ctx, "pdegpu_oflow_sor_elin4_2d_batch", PDEGPU_FLOW_ELIN4, U_out, V_out,
+                           U, V, nullptr, nullptr, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, nrows, ncols, batch, iter, omega, solver);
+}
+
+extern "C" int pdegpu_oflow_sor_llin4_2d_batch(pdegpu_ctx *ctx, float *dU_out, float *dV_out,
+        const float *U, const float *V, const float *dU, const float *dV, const float *M,
+        const float *Cu, const float *Cv, const float *Du, const float *Dv,
+        const float *wW, const float *wN, const float *wE, const float *wS,
+        int nrows, int ncols, int batch, float iter, float omega, int solver)
+{
+    if (!ctx) return PDEGPU_ERR_ARG;
+    NULLCHECK("pdegpu_oflow_sor_llin4_2d_batch", dU_out, dV_out, U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS);
+    return flow_sor4_batch(ctx, "pdegpu_oflow_sor_llin4_2d_batch", PDEGPU_FLOW_LLIN4, dU_out, dV_out,
+                           U, V, dU, dV, M, Cu, Cv, Du, Dv, wW, wN, wE, wS, nrows, ncols, batch, iter, omega, solver);
 }
 
 extern "C" int pdegpu_oflow_sor_llin8_2d(pdegpu_ctx *ctx,
@@ -560,13 +635,12 @@ extern "C" int pdegpu_dev_llin_solve(pdegpu_ctx *ctx, const pdegpu_llin_terms *t
         const int rc = relax_llin_fused(ctx, &sys, &tt, iter, omega, ctx->sweep_order == PDEGPU_ORDER_REFERENCE);
         if (rc != PDEGPU_ERR_UNSUPPORTED) return rc;
     }
-    float *Us = work, *Vs = work + all, *w[4], *T[5];
+    float *w[4], *T[5];
     for (int k = 0; k < 4; k++) w[k] = work + (2 + k) * all;
     for (int k = 0; k < 5; k++) { T[k] = work + (6 + k) * all; tt.out[k] = T[k]; }
     int rc;
-    if ((rc = op_axpby(ctx, Us, 1.0f, U, 1.0f, dU, all))) return rc;
-    if ((rc = op_axpby(ctx, Vs, 1.0f, V, 1.0f, dV, all))) return rc;
-    if ((rc = op_opdiff(ctx, w[0], w[1], w[2], w[3], Us, Vs, t->nrows, t->ncols, t->batch, n))) return rc;       // [wW wN wS wE]
+    // OPdiffWeights(U+dU, V+dV): the sums are formed inside the weight kernel (no U+dU, V+dV arrays)    [wW wN wS wE]
+    if ((rc = op_opdiff_sum(ctx, w[0], w[1], w[2], w[3], U, V, dU, dV, t->nrows, t->ncols, t->batch, n))) return rc;
     if ((rc = op_llin_terms(ctx, &tt))) return rc;
     sys.m = T[0]; sys.c[0] = T[1]; sys.c[1] = T[2]; sys.d[0] = T[3]; sys.d[1] = T[4];
     sys.w[W_W] = w[0]; sys.w[W_N] = w[1]; sys.w[W_S] = w[2]; sys.w[W_E] = w[3];

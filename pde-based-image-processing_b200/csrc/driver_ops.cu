@@ -38,14 +38,16 @@ __device__ __forceinline__ int mirrori(int v, int n)            // 'symmetric' p
 // ---------------------------------------------------------------------------------------------
 // OPdiffWeights (double precision, circshift wrap) -> 4 single fields
 // ---------------------------------------------------------------------------------------------
+// (dU, dV given: the weights of U + dU, V + dV -- the sums are formed on the fly, FlowEminND_llin_2D_v10.m:321)
 __global__ void __launch_bounds__(256)
 op_diff_weights_kernel(float *__restrict__ wW, float *__restrict__ wN, float *__restrict__ wS, float *__restrict__ wE,
-                       const float *__restrict__ U, const float *__restrict__ V, int nr, int nc, long long stride)
+                       const float *__restrict__ U, const float *__restrict__ V, const float *__restrict__ dU, const float *__restrict__ dV,
+                       int nr, int nc, long long stride)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= nr) return;
     const long long base = (long long)blockIdx.z * stride;
-    const OpdiffSrc src = {U + base, V + base, nullptr, nullptr};
+    const OpdiffSrc src = {U + base, V + base, dU ? dU + base : nullptr, dV ? dV + base : nullptr};
     const long long p = base + (long long)j * nr + i;
     opdiff_at(src, i, j, nr, nc, wW[p], wN[p], wS[p], wE[p]);
 }
@@ -339,8 +341,14 @@ inline dim3 grid2(int nr, int nc, int planes) { return dim3((nr + 255) / 256, nc
 int op_opdiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V,
               int nr, int nc, int batch, long long stride)
 {
-    PDEGPU_PROF(ctx, "op_diff_weights_kernel", 24.0 * nr * nc * batch);
-    op_diff_weights_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(wW, wN, wS, wE, U, V, nr, nc, stride);
+    return op_opdiff_sum(ctx, wW, wN, wS, wE, U, V, nullptr, nullptr, nr, nc, batch, stride);
+}
+
+int op_opdiff_sum(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V, const float *dU, const float *dV,
+                  int nr, int nc, int batch, long long stride)
+{
+    PDEGPU_PROF(ctx, "op_diff_weights_kernel", (dU ? 32.0 : 24.0) * nr * nc * batch);
+    op_diff_weights_kernel<<<grid2(nr, nc, batch), 256, 0, ctx->stream>>>(wW, wN, wS, wE, U, V, dU, dV, nr, nc, stride);
     PDEGPU_LAUNCH_CHECK(ctx, "op_diff_weights_kernel");
     return PDEGPU_OK;
 }

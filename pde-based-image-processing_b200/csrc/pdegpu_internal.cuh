@@ -163,6 +163,8 @@ int op_ddiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wE, float *wS, const 
 
 // driver-side stencils (driver_ops.cu)
 int op_opdiff(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V, int nr, int nc, int batch, long long stride);
+int op_opdiff_sum(pdegpu_ctx *ctx, float *wW, float *wN, float *wS, float *wE, const float *U, const float *V, const float *dU, const float *dV,
+                  int nr, int nc, int batch, long long stride);   // weights of (U + dU, V + dV), sums formed on the fly
 int op_llin_terms(pdegpu_ctx *ctx, const pdegpu_llin_terms *t);
 int op_elin_terms(pdegpu_ctx *ctx, const pdegpu_elin_terms *t);
 int op_disp_sym_terms(pdegpu_ctx *ctx, const pdegpu_disp_sym_terms *t);

@@ -280,6 +280,25 @@ class Context:
     def lhs(self, sys: System, nframes: int, AU: int, AV: int):
         self._chk(dll().pdegpu_dev_lhs(self.h, ctypes.byref(sys), nframes, AU, AV))
 
+    def oflow_sor_batch(self, fields: dict, late: bool, iters: int, omega: float, solver: int):
+        """pdegpu_oflow_sor_{llin4,elin4}_2d_batch: `fields` maps the gateway's argument names (U, V, (dU, dV,) M, Cu, Cv,
+        Du, Dv, wW, wN, wE, wS) to numpy arrays [batch, rows, cols] (single). Returns the two relaxed unknowns with the
+        same shape. Host-pointer entry point: chunked uploads, sweeps and downloads overlap inside the call."""
+        import numpy as np
+        keys = (("U", "V", "dU", "dV") if late else ("U", "V")) + ("M", "Cu", "Cv", "Du", "Dv", "wW", "wN", "wE", "wS")
+        B, nr, nc = fields["U"].shape
+        # system b of every array at offset b*nr*nc, each system column-major like the MEX arrays
+        flat = [np.ascontiguousarray(np.asarray(fields[k], np.float32).transpose(0, 2, 1)).reshape(-1) for k in keys]
+        assert all(a.size == B * nr * nc for a in flat)
+        o0, o1 = np.empty(B * nr * nc, np.float32), np.empty(B * nr * nc, np.float32)
+        fn = dll().pdegpu_oflow_sor_llin4_2d_batch if late else dll().pdegpu_oflow_sor_elin4_2d_batch
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p] * (3 + len(keys)) + [ctypes.c_int] * 3 + [c_float] * 2 + [ctypes.c_int]
+        self._chk(fn(self.h, o0.ctypes.data, o1.ctypes.data, *[a.ctypes.data for a in flat], nr, nc, B,
+                     c_float(iters), c_float(omega), solver))
+        back = lambda a: a.reshape(B, nc, nr).transpose(0, 2, 1)
+        return back(o0), back(o1)
+
     def tvdenoise8(self, I, **overrides):
         """Iout = TVdenoise8(I): I numpy [rows, cols(, frames)] single. Host-pointer entry point."""
         import numpy as np
