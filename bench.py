@@ -80,10 +80,10 @@ def parse():
     ap.add_argument("--band-T", type=int, default=4, help="sweeps per halo exchange (halo = 2T columns)")
     ap.add_argument("--band-leg", type=int, default=1, help="one band-n x band-n image in column bands as a leg of the default line (0 = skip)")
     ap.add_argument("--batch512", type=int, default=512, help="1080p pairs of the configs[4] batch leg, split over the GPUs (0 = skip)")
-    ap.add_argument("--flow-batch", type=int, default=16, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
+    ap.add_argument("--flow-batch", type=int, default=64, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
     ap.add_argument("--flow-ref-batch", type=int, default=256, help="640x480 pairs per GPU for the flows/s leg in the reference's line order (0 = skip)")
     ap.add_argument("--sweep-legs", type=int, default=1, help="relaxation sweep alone at 1080p / 4096x2160 / point solver (0 = skip)")
-    ap.add_argument("--fmg-pairs", type=int, default=32, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
+    ap.add_argument("--fmg-pairs", type=int, default=64, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
     return ap.parse_args()
 
 
@@ -331,7 +331,7 @@ def flows_leg(ctx, dev, stream, dist, world, rank, FB, reps=5, order=None, cpu=T
 # FMG leg: BASELINE configs[2], the whole FlowEminNDFASFMG_elin_2D_v10 driver (early linearisation, full multigrid,
 # one FAS V-cycle per level, firstLoop=4, ALR iter=4) on synthetic 1920x1080 pairs, device resident and end to end
 # ---------------------------------------------------------------------------------------------
-def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=5):
+def fmg_leg(ctx, dev, stream, dist, world, rank, FB, reps=3):
     import torch
     from pdegpu import lib, synth
     NR, NC, C = 1080, 1920, 1                      # runme.m:90 runs this driver on single-channel frames

@@ -169,9 +169,13 @@ extern "C" void pdegpu_free(pdegpu_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 // lanes (pdegpu_internal.cuh)
 // ---------------------------------------------------------------------------------------------
-int pdegpu_lane_count(pdegpu_ctx *ctx, int batch)
+int pdegpu_lane_count(pdegpu_ctx *ctx, int batch, bool serial_order)
 {
-    static const int max_lanes = getenv("PDEGPU_LANES") ? atoi(getenv("PDEGPU_LANES")) : 32;
+    // zebra / red-black kernels fill the GPU from one problem: 32 lanes only hide the launch-bound coarse levels. The
+    // reference-order kernels run ONE CTA per problem -- there the lanes ARE the parallelism (FMG 1080p: 4.3 / 18.0 / 34.5
+    // flows/s with 8 / 32 / 64 pairs side by side), at one workspace per lane (0.67 GB per 1080p pair)
+    static const int env_lanes = getenv("PDEGPU_LANES") ? atoi(getenv("PDEGPU_LANES")) : 0;
+    const int max_lanes = env_lanes > 0 ? env_lanes : (serial_order ? 64 : 32);
     if (ctx->prof_on || ctx->parent || batch < 2 || max_lanes < 2) return 1;
     const int cap = (int)(sizeof(ctx->lanes) / sizeof(ctx->lanes[0]));
     int n = batch < max_lanes ? batch : max_lanes;

@@ -42,7 +42,7 @@ struct pdegpu_ctx {
     // LANES: child contexts (own stream, scratch, workspace) on which the pairs of a batch run side by side where a
     // driver pipeline is written for one pair (FMG, Horn-Schunck, symmetric stereo): see pdegpu_lanes_* below
     struct pdegpu_ctx *parent;
-    struct pdegpu_ctx *lanes[32];
+    struct pdegpu_ctx *lanes[128];  // 128 = the device's limit of concurrently resident grids
     int           nlanes;
     cudaEvent_t   ev_fork, ev_join;
     char          err[512];
@@ -53,7 +53,7 @@ struct pdegpu_ctx {
 // settings and own at least `work_bytes` of workspace each. fork / join: the lanes' streams wait for everything
 // enqueued on the context's stream / the context's stream waits for the lanes (both legal inside a stream capture:
 // the captured graph then has one branch per lane).
-int pdegpu_lane_count(pdegpu_ctx *ctx, int batch);
+int pdegpu_lane_count(pdegpu_ctx *ctx, int batch, bool serial_order = false);   // serial_order: the line sweeps run in the reference's order
 int pdegpu_lanes_prepare(pdegpu_ctx *ctx, int n, size_t work_bytes, const char *who);
 int pdegpu_lanes_fork(pdegpu_ctx *ctx, int n);
 int pdegpu_lanes_join(pdegpu_ctx *ctx, int n);

@@ -298,7 +298,7 @@ extern "C" int pdegpu_dev_flow_fmg_2d(pdegpu_ctx *ctx, float *U, float *V, const
     int rc = fmg_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
     // pairs of a batch run side by side on the context's lanes (one workspace each); a single pair on the context itself
-    const int K = pdegpu_lane_count(ctx, batch);
+    const int K = pdegpu_lane_count(ctx, batch, ctx->sweep_order == PDEGPU_ORDER_REFERENCE || (ctx->sweep_order == PDEGPU_ORDER_AUTO && params->solver == 2));
     if ((rc = K > 1 ? pdegpu_lanes_prepare(ctx, K, dry.peak, "pdegpu_dev_flow_fmg_2d") : pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_fmg_2d"))) return rc;
     struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_fmg_params P; char *work; int id, K; };
     Args a;
@@ -455,7 +455,7 @@ extern "C" int pdegpu_dev_flow_hs_2d(pdegpu_ctx *ctx, float *U, float *V, const 
     int rc = hs_run(ctx, dry, U, V, I0, I1, nrows, ncols, channels, *params);
     if (rc) return rc;
     // pairs of a batch run side by side on the context's lanes (one workspace each); a single pair on the context itself
-    const int K = pdegpu_lane_count(ctx, batch);
+    const int K = pdegpu_lane_count(ctx, batch, ctx->sweep_order == PDEGPU_ORDER_REFERENCE || (ctx->sweep_order == PDEGPU_ORDER_AUTO && params->solver == 2));
     if ((rc = K > 1 ? pdegpu_lanes_prepare(ctx, K, dry.peak, "pdegpu_dev_flow_hs_2d") : pdegpu_work_reserve(ctx, dry.peak, "pdegpu_dev_flow_hs_2d"))) return rc;
     struct Args { pdegpu_ctx *ctx; float *U, *V; const float *I0, *I1; int nrows, ncols, channels, batch; pdegpu_flow_hs_params P; char *work; int id, K; };
     Args a;

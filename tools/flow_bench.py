@@ -23,7 +23,9 @@ L = lib.dll()
 p = lib.FlowLlinParams(); L.pdegpu_flow_llin_default_params(ctypes.byref(p))
 def run():
     ctx._chk(L.pdegpu_dev_flow_llin_2d(ctx.h, U.data_ptr(), V.data_ptr(), a0.data_ptr(), a1.data_ptr(), nr, nc, C, B, ctypes.byref(p)))
-run(); ctx.sync()
+for _ in range(3):      # direct run, graph capture, first replay
+    run()
+ctx.sync()
 n0 = ctx.launches
 t0 = time.perf_counter()
 for _ in range(reps):
