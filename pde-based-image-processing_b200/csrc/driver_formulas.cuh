@@ -101,4 +101,28 @@ __device__ __forceinline__ void opdiff_at(const OpdiffSrc &s, int i, int j, int 
     wS = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(sS, 0.00001)));
 }
 
+// The east and south weights of pixel (i, j) only. The weight of an edge does not depend on the side it is seen from:
+// sE(i, j) and sW(i, j+1) are sums of the same four squares (a difference and its negative, a sum in either order), so
+// wW(i, j+1) = wE(i, j) and wN(i+1, j) = wS(i, j) bit for bit (indices wrap like circshift). The stand-alone kernel
+// computes each edge once and stores it on both sides: half the double-precision square roots and divisions.
+__device__ __forceinline__ void opdiff_east_south_at(const OpdiffSrc &s, int i, int j, int nr, int nc, float &wE, float &wS)
+{
+    auto P = [&](int ii, int jj) -> long long { return (long long)jj * nr + ii; };
+    auto qd = [](double a, double b) { return __dadd_rn(__dmul_rn(0.25, a), __dmul_rn(-0.25, b)); };
+    auto uver = [&](int ii, int jj) { return qd(s.u(P(df_clampi(ii - 1, 0, nr - 1), jj)), s.u(P(df_clampi(ii + 1, 0, nr - 1), jj))); };
+    auto vver = [&](int ii, int jj) { return qd(s.v(P(df_clampi(ii - 1, 0, nr - 1), jj)), s.v(P(df_clampi(ii + 1, 0, nr - 1), jj))); };
+    auto uhor = [&](int ii, int jj) { return qd(s.u(P(ii, df_clampi(jj - 1, 0, nc - 1))), s.u(P(ii, df_clampi(jj + 1, 0, nc - 1)))); };
+    auto vhor = [&](int ii, int jj) { return qd(s.v(P(ii, df_clampi(jj - 1, 0, nc - 1))), s.v(P(ii, df_clampi(jj + 1, 0, nc - 1)))); };
+    auto sq = [](double x) { return __dmul_rn(x, x); };
+    auto edge = [&](double du_, double gu, double dv_, double gv) {
+        return __dadd_rn(__dadd_rn(__dadd_rn(sq(du_), sq(gu)), sq(dv_)), sq(gv));
+    };
+    const int je = df_wrapi(j + 1, nc), is = df_wrapi(i + 1, nr);
+    const double u0 = s.u(P(i, j)), v0 = s.v(P(i, j));
+    const double sE = edge(__dsub_rn(s.u(P(i, je)), u0), __dadd_rn(uver(i, j), uver(i, je)), __dsub_rn(s.v(P(i, je)), v0), __dadd_rn(vver(i, j), vver(i, je)));
+    const double sS = edge(__dsub_rn(s.u(P(is, j)), u0), __dadd_rn(uhor(i, j), uhor(is, j)), __dsub_rn(s.v(P(is, j)), v0), __dadd_rn(vhor(i, j), vhor(is, j)));
+    wE = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(sE, 0.00001)));
+    wS = (float)__ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(sS, 0.00001)));
+}
+
 }  // namespace

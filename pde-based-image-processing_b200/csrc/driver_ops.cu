@@ -48,8 +48,14 @@ op_diff_weights_kernel(float *__restrict__ wW, float *__restrict__ wN, float *__
     if (i >= nr) return;
     const long long base = (long long)blockIdx.z * stride;
     const OpdiffSrc src = {U + base, V + base, dU ? dU + base : nullptr, dV ? dV + base : nullptr};
-    const long long p = base + (long long)j * nr + i;
-    opdiff_at(src, i, j, nr, nc, wW[p], wN[p], wS[p], wE[p]);
+    // every edge once, stored on both of its sides (opdiff_east_south_at): each wW / wN element has exactly one writer
+    float e, s;
+    opdiff_east_south_at(src, i, j, nr, nc, e, s);
+    const long long col = base + (long long)j * nr, ecol = base + (long long)df_wrapi(j + 1, nc) * nr;
+    wE[col + i] = e;
+    wS[col + i] = s;
+    wW[ecol + i] = e;
+    wN[col + df_wrapi(i + 1, nr)] = s;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -40,6 +40,8 @@ def test_op_diff_weights(steps, shape):
     o = ms.op_diff_weights(U, V)
     for a, b in zip(g, o):
         assert close(a, b.astype(np.float32), 1e-6)
+    # every edge is computed once and stored on both of its sides (returned order: wW, wN, wS, wE)
+    assert np.array_equal(g[0], np.roll(g[3], 1, axis=1)) and np.array_equal(g[1], np.roll(g[2], 1, axis=0))
 
 
 @pytest.mark.parametrize("second", ["none", "first", "gradmag"])

@@ -121,3 +121,15 @@ def test_interp2_rows_matches_numpy_interp():
         want = np.interp(xq[r][inside].astype(np.float64), np.arange(1, 32), vals[r].astype(np.float64))
         np.testing.assert_allclose(got[r][inside], want, rtol=2e-6, atol=2e-6)
         assert np.isnan(got[r][~inside]).all()               # interp2 returns NaN outside the grid
+
+
+@pytest.mark.parametrize("shape", [(37, 53), (3, 5), (16, 16)])
+def test_op_diff_weights_edges_look_the_same_from_both_sides(shape):
+    """FlowEminND_llin_2D_v10.m:389-433: the weight of an edge is a sum of the same four squares whichever end it is
+    seen from (a difference and its negative, a sum in either order), so wW = circshift(wE, [0 1]) and
+    wN = circshift(wS, [1 0]) BIT FOR BIT. op_diff_weights_kernel relies on it (every edge computed once, stored twice);
+    tests/test_gpu_driver_steps.py holds the kernel to the per-pixel formula through the fused path."""
+    U, V = rng.standard_normal(shape).astype(np.float32), rng.standard_normal(shape).astype(np.float32)
+    wW, wN, wS, wE = ms.op_diff_weights(U, V)
+    assert np.array_equal(wW, np.roll(wE, 1, axis=1))
+    assert np.array_equal(wN, np.roll(wS, 1, axis=0))
