@@ -13,8 +13,10 @@ more than the 126 MB L2 (no cache-resident re-use between steps).
 
 One step = one pass of the hot path over the whole batch = batch x iter line-relaxation iterations.
 value = Mpix*iter/s over all ranks, inputs resident in HBM (device pointers, C ABI).
-e2e   = the same metric through the drop-in host-pointer C-ABI call (pdegpu_oflow_sor_llin4_2d),
-        pinned host buffers, H2D + D2H inside the timed region.
+e2e   = the same metric on the same batch from pinned HOST buffers through the C ABI
+        (pdegpu_oflow_sor_llin4_2d_batch: one call per step, H2D of every operand + D2H of the result inside the
+        timed region, chunks overlapped inside the call); e2e.single_call = the gateway's own entry point
+        (pdegpu_oflow_sor_llin4_2d), one system per synchronous call.
 roofline = dominant kernel: algorithmic bytes (60 B/px/sweep for llin4, one ALR iteration
         = 2 sweeps) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline = the reference's own CPU code (oracle/_ref, compiled unmodified) on the box's host cores.

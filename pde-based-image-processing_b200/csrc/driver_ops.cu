@@ -211,21 +211,21 @@ struct ResizeArgs {
     long long istride, ostride;
 };
 
-__global__ void __launch_bounds__(256)
-imresize_kernel(float *__restrict__ out, const float *__restrict__ in, const ResizeArgs a)
+// The contributions of an output coordinate (first input index `left`, P normalised weights) depend on that coordinate
+// only -- not on the position along the other dimension, the plane or the pair of a batch. A small kernel tabulates them
+// (double-precision kernel evaluations and one division per tap: the expensive part), the resize kernel proper is then
+// P multiply-adds per pixel. Same expressions, same order of accumulation as the one-kernel form it replaces.
+__global__ void __launch_bounds__(128)
+imresize_table_kernel(double *__restrict__ wtab, int *__restrict__ ltab, const ResizeArgs a, const int P)
 {
-    // output pixel (i, j) of an onr x onc plane
-    const int onr = a.dim == 0 ? a.out_len : a.other, inr = a.dim == 0 ? a.in_len : a.other;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (i >= onr) return;
-    in += (long long)blockIdx.z * a.istride;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;      // 0-based output coordinate along a.dim
+    if (t >= a.out_len) return;
     const bool shrink = a.scale < 1.0 && a.antialias;
     const double kw0 = a.cubic ? 4.0 : 2.0;
     const double kw = shrink ? kw0 / a.scale : kw0;
-    const int x = (a.dim == 0 ? i : j) + 1;                   // 1-based output coordinate
+    const int x = t + 1;                                      // 1-based output coordinate
     const double u = (double)x / a.scale + 0.5 * (1.0 - 1.0 / a.scale);
-    const int left = (int)floor(u - kw / 2.0);
-    const int P = (int)ceil(kw) + 2;
+    const int left = (int)floor(u - kw / 2.0);              // P = ceil(kw) + 2 taps (computed once, on the host)
     auto h = [&](double d) -> double {
         if (shrink) d *= a.scale;
         const double ax = fabs(d);
@@ -237,14 +237,28 @@ imresize_kernel(float *__restrict__ out, const float *__restrict__ in, const Res
         } else f = fmax(0.0, 1.0 - ax);
         return shrink ? a.scale * f : f;
     };
-    double wsum = 0.0, acc = 0.0;
+    double wsum = 0.0;
     for (int p = 0; p < P; p++) wsum += h(u - (double)(left + p));
+    for (int p = 0; p < P; p++) wtab[(long long)p * a.out_len + t] = h(u - (double)(left + p)) / wsum;   // tap-major: coalesced along i
+    ltab[t] = left;
+}
+
+__global__ void __launch_bounds__(256)
+imresize_kernel(float *__restrict__ out, const float *__restrict__ in, const ResizeArgs a,
+                const double *__restrict__ wtab, const int *__restrict__ ltab, int P)
+{
+    // output pixel (i, j) of an onr x onc plane
+    const int onr = a.dim == 0 ? a.out_len : a.other, inr = a.dim == 0 ? a.in_len : a.other;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= onr) return;
+    in += (long long)blockIdx.z * a.istride;
+    const int t = a.dim == 0 ? i : j;
+    const int left = ltab[t];
+    double acc = 0.0;
     for (int p = 0; p < P; p++) {
-        const int ind = left + p;                             // 1-based input coordinate
-        const double w = h(u - (double)ind) / wsum;
-        const int src = mirrori(ind - 1, a.in_len);
+        const int src = mirrori(left + p - 1, a.in_len);      // left + p: 1-based input coordinate
         const float v = a.dim == 0 ? in[(long long)j * inr + src] : in[(long long)src * inr + i];
-        acc += w * (double)v;
+        acc += wtab[(long long)p * a.out_len + t] * (double)v;
     }
     out[(long long)blockIdx.z * a.ostride + (long long)j * onr + i] = (float)acc;
 }
@@ -437,8 +451,19 @@ int op_imresize_dim(pdegpu_ctx *ctx, float *out, const float *in, int dim, int i
     a.dim = dim; a.in_len = in_len; a.out_len = out_len; a.other = other; a.scale = scale; a.antialias = antialias;
     a.istride = istride; a.ostride = ostride;
     const int onr = dim == 0 ? out_len : other, onc = dim == 0 ? other : out_len;
+    const double kw0 = cubic ? 4.0 : 2.0;
+    const int P = (int)ceil((scale < 1.0 && antialias) ? kw0 / scale : kw0) + 2;
+    // table of contributions in the context's scratch (stream-ordered with the sweeps that use the same buffer)
+    const size_t wbytes = ((size_t)out_len * P * sizeof(double) + 255) & ~(size_t)255;
+    int rc = pdegpu_scratch_reserve(ctx, wbytes + (size_t)out_len * sizeof(int));
+    if (rc) return rc;
+    double *wtab = (double *)ctx->scratch;
+    int *ltab = (int *)(ctx->scratch + wbytes);
+    PDEGPU_PROF(ctx, "imresize_table_kernel", 0.0);
+    imresize_table_kernel<<<(out_len + 127) / 128, 128, 0, ctx->stream>>>(wtab, ltab, a, P);
+    PDEGPU_LAUNCH_CHECK(ctx, "imresize_table_kernel");
     PDEGPU_PROF(ctx, "imresize_kernel", 4.0 * ((double)in_len + out_len) * other * planes);
-    imresize_kernel<<<grid2(onr, onc, planes), 256, 0, ctx->stream>>>(out, in, a);
+    imresize_kernel<<<grid2(onr, onc, planes), 256, 0, ctx->stream>>>(out, in, a, wtab, ltab, P);
     PDEGPU_LAUNCH_CHECK(ctx, "imresize_kernel");
     return PDEGPU_OK;
 }
