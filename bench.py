@@ -85,7 +85,10 @@ def parse():
     ap.add_argument("--flow-batch", type=int, default=64, help="640x480 pairs per GPU for the flows/s leg (0 = skip)")
     ap.add_argument("--flow-ref-batch", type=int, default=256, help="640x480 pairs per GPU for the flows/s leg in the reference's line order (0 = skip)")
     ap.add_argument("--sweep-legs", type=int, default=1, help="relaxation sweep alone at 1080p / 4096x2160 / point solver (0 = skip)")
-    ap.add_argument("--fmg-pairs", type=int, default=64, help="1920x1080 pairs per GPU for the FMG leg (0 = skip)")
+    ap.add_argument("--fmg-pairs", type=int, default=32,
+                    help="1920x1080 pairs per GPU for the FMG leg (0 = skip). In the reference's order throughput is proportional to the pairs "
+                         "side by side (64: 35.0 flows/s, profiles/r02g_bench_1gpu.json) -- and so is the warm-up of the leg: the default "
+                         "keeps the whole bench at three minutes")
     return ap.parse_args()
 
 
